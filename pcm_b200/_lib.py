@@ -1,0 +1,85 @@
+"""ctypes binding of libpcm_b200.so (the C ABI declared in include/pcm_b200.h).
+
+The product path has no CPU fallback: if the shared library is missing the import of any op
+fails loudly with instructions to run ``python -c "import __graft_entry__ as g; g.build()"``.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libpcm_b200.so")
+
+MAX_ASRC, MAX_BSRC, MAX_PROG = 4, 2, 24
+
+
+class ASrc(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("C", C.c_int32), ("W", C.c_int32), ("H", C.c_int32),
+                ("B", C.c_int32), ("sW", C.c_int64), ("sH", C.c_int64), ("sB", C.c_int64)]
+
+
+class BSrc(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("K", C.c_int32), ("N", C.c_int32), ("ld", C.c_int64)]
+
+
+class KEntry(C.Structure):
+    _fields_ = [("a_src", C.c_int32), ("b_src", C.c_int32), ("dw", C.c_int32), ("dh", C.c_int32),
+                ("nchunks", C.c_int32), ("a_c0", C.c_int32), ("b_k0", C.c_int32), ("pad_", C.c_int32)]
+
+
+class GemmDesc(C.Structure):
+    _fields_ = [
+        ("a", ASrc * MAX_ASRC), ("b", BSrc * MAX_BSRC), ("prog", KEntry * MAX_PROG),
+        ("num_a", C.c_int32), ("num_b", C.c_int32), ("num_prog", C.c_int32),
+        ("lin", C.c_int32), ("M", C.c_int32), ("N", C.c_int32),
+        ("geoW", C.c_int32), ("geoH", C.c_int32), ("block_n", C.c_int32),
+        ("out", C.c_void_p), ("bias", C.c_void_p), ("rowvec", C.c_void_p), ("residual", C.c_void_p),
+        ("osW", C.c_int64), ("osH", C.c_int64), ("osB", C.c_int64), ("rowvec_ld", C.c_int64),
+        ("epiW", C.c_int32), ("epiHW", C.c_int32), ("out_fp32", C.c_int32), ("round_bf16", C.c_int32),
+        ("alpha", C.c_float), ("act", C.c_int32),
+    ]
+
+
+class WgradDesc(C.Structure):
+    _fields_ = [
+        ("p", ASrc), ("q", ASrc), ("q_c0", C.c_int32), ("lin", C.c_int32), ("M", C.c_int32),
+        ("geoW", C.c_int32), ("geoH", C.c_int32), ("num_taps", C.c_int32),
+        ("dw", C.c_int32 * 9), ("dh", C.c_int32 * 9), ("tap_off", C.c_int64 * 9),
+        ("out", C.c_void_p), ("os_row", C.c_int64), ("os_col", C.c_int64),
+        ("ksplit", C.c_int32), ("alpha", C.c_float),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: the pcm_b200 CUDA extension is not built. "
+                "Run `python -c \"import __graft_entry__ as g; g.build()\"` (needs nvcc). "
+                "There is no CPU fallback for the product path.")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.pcm_last_error.restype = C.c_char_p
+        for name in EXPORTS:
+            fn = getattr(_lib, name)
+            if name not in ("pcm_last_error",):
+                fn.restype = C.c_int
+    return _lib
+
+
+# every symbol include/pcm_b200.h declares (checked by tests/test_abi.py)
+EXPORTS = [
+    "pcm_last_error", "pcm_version", "pcm_num_sms", "pcm_gemm", "pcm_wgrad",
+]
+
+
+class PcmError(RuntimeError):
+    pass
+
+
+def check(rc, what=""):
+    if rc != 0:
+        raise PcmError(f"{what} failed ({rc}): {lib().pcm_last_error().decode()}")

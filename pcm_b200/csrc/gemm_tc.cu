@@ -1,0 +1,560 @@
+// tcgen05 / TMEM / TMA implicit-GEMM for sm_100a.
+//
+//   pcm_gemm  : out[M, N] = alpha * sum_k A[m, k] * Bw[n, k]  (+bias, +per-image row vector,
+//               +residual, optional SiLU).  A is gathered by TMA from up to 4 NHWC bf16 tensors
+//               through a "K program" (spatial taps x channel chunks x K segments), so the same
+//               kernel runs nn.Linear, 1x1 / 3x3 / stride-2 convolutions (parity planes),
+//               skip-concat convolutions (two K segments), the LoRA up-projection fused as an
+//               extra 64-wide K segment, and all of their dgrads (taps mirrored, W transposed).
+//   pcm_wgrad : out[ch, r] += alpha * sum_m P[m(+tap), ch] * Q[m, r]   (LoRA A/B weight grads),
+//               both operands MN-major straight from the activation layout, split over tokens.
+//
+// Replaces the cuDNN / cuBLAS calls that diffusers' UNet2DConditionModel + peft LoRA issue for
+// train_pcm_lora_sd15.py:1192-1198, 1219-1223, 1238-1244, 1263-1268 (forwards) and :1296
+// (backward).  Warp roles: warp0 = TMA producer, warp1 = MMA issuer (+TMEM alloc),
+// warps2-5 = epilogue (TMEM -> registers -> global).
+#include "common.cuh"
+#include "host_common.h"
+#include "../../include/pcm_b200.h"
+
+namespace pcm {
+
+struct KEntry {
+  int a_map, b_map, dw, dh, nchunks, a_c0, b_k0, pad_;
+};
+
+struct alignas(64) GemmParams {
+  CUtensorMap a_maps[PCM_MAX_ASRC];
+  CUtensorMap b_maps[PCM_MAX_BSRC];
+  KEntry prog[PCM_MAX_PROG];
+  int num_prog, lin;
+  int M, N;
+  int geoW, geoHW;
+  int block_n, tiles_m, tiles_n, num_kblocks, num_stages;
+  void* out;
+  const float* bias;
+  const bf16* rowvec;
+  const bf16* residual;
+  long long osW, osH, osB, rowvec_ld;
+  int epiW, epiHW;
+  int out_fp32, round_bf16;
+  float alpha;
+  int act;
+};
+
+constexpr int kGemmThreads = 192;
+constexpr int kMaxStages = 8;
+constexpr int kATileBytes = 128 * 128;  // 128 rows x 64 bf16
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+pcm_gemm_kernel(const __grid_constant__ GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t tfull_bar[2];
+  __shared__ __align__(8) uint64_t tempty_bar[2];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int S = p.num_stages;
+  const uint32_t stage_bytes = kATileBytes + p.block_n * 128;
+  const int num_tiles = p.tiles_m * p.tiles_n;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < PCM_MAX_ASRC; ++i) tma_prefetch_desc(&p.a_maps[i]);
+    for (int i = 0; i < PCM_MAX_BSRC; ++i) tma_prefetch_desc(&p.b_maps[i]);
+    for (int i = 0; i < S; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_base_smem, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
+        const int m0 = tm * 128, n0 = tn * p.block_n;
+        int b0 = 0, h0 = 0;
+        if (!p.lin) {
+          b0 = m0 / p.geoHW;
+          h0 = (m0 - b0 * p.geoHW) / p.geoW;
+        }
+        for (int e = 0; e < p.num_prog; ++e) {
+          const KEntry en = p.prog[e];
+          for (int c = 0; c < en.nchunks; ++c) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
+            uint8_t* sa = smem + stage * stage_bytes;
+            uint8_t* sb = sa + kATileBytes;
+            if (p.lin)
+              tma_load_4d(sa, &p.a_maps[en.a_map], &full_bar[stage], en.a_c0 + c * 64, m0, 0, 0);
+            else
+              tma_load_4d(sa, &p.a_maps[en.a_map], &full_bar[stage], en.a_c0 + c * 64, en.dw,
+                          h0 + en.dh, b0);
+            tma_load_2d(sb, &p.b_maps[en.b_map], &full_bar[stage], en.b_k0 + c * 64, n0);
+            if (++stage == S) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, p.block_n, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 256;
+        for (int kb = 0; kb < p.num_kblocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
+          const uint32_t b_addr = a_addr + kATileBytes;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t ad = umma_desc_sw128(a_addr + k * 32, 16, 1024);
+            const uint64_t bd = umma_desc_sw128(b_addr + k * 32, 16, 1024);
+            umma_f16(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == S) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull_bar[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
+      const int m = tm * 128 + row, n0 = tn * p.block_n;
+      const bool valid = m < p.M;
+      long long off = 0;
+      const bf16* rv = nullptr;
+      if (valid) {
+        const int b = m / p.epiHW;
+        const int r = m - b * p.epiHW;
+        const int h = r / p.epiW;
+        const int w = r - h * p.epiW;
+        off = b * p.osB + h * p.osH + w * p.osW;
+        if (p.rowvec) rv = p.rowvec + b * p.rowvec_ld;
+      }
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256;
+      for (int j = 0; j < p.block_n; j += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + j, v);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int n = n0 + j + g * 8;
+            if (n >= p.N) break;
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[g * 8 + i]) * p.alpha;
+            if (n + 8 <= p.N) {
+              if (p.bias) {
+                const float4 b0 = *reinterpret_cast<const float4*>(p.bias + n);
+                const float4 b1 = *reinterpret_cast<const float4*>(p.bias + n + 4);
+                f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+              }
+              if (rv) {
+                const uint4 u = *reinterpret_cast<const uint4*>(rv + n);
+                float2 t;
+                t = unpack_bf16x2(u.x); f[0] += t.x; f[1] += t.y;
+                t = unpack_bf16x2(u.y); f[2] += t.x; f[3] += t.y;
+                t = unpack_bf16x2(u.z); f[4] += t.x; f[5] += t.y;
+                t = unpack_bf16x2(u.w); f[6] += t.x; f[7] += t.y;
+              }
+              if (p.residual) {
+                const uint4 u = *reinterpret_cast<const uint4*>(p.residual + off + n);
+                float2 t;
+                t = unpack_bf16x2(u.x); f[0] += t.x; f[1] += t.y;
+                t = unpack_bf16x2(u.y); f[2] += t.x; f[3] += t.y;
+                t = unpack_bf16x2(u.z); f[4] += t.x; f[5] += t.y;
+                t = unpack_bf16x2(u.w); f[6] += t.x; f[7] += t.y;
+              }
+              if (p.act == 1) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] = silu_f(f[i]);
+              }
+              if (p.out_fp32) {
+                if (p.round_bf16) {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) f[i] = __bfloat162float(__float2bfloat16_rn(f[i]));
+                }
+                float* o = reinterpret_cast<float*>(p.out) + off + n;
+                *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
+                *reinterpret_cast<float4*>(o + 4) = make_float4(f[4], f[5], f[6], f[7]);
+              } else {
+                uint4 u;
+                u.x = pack_bf16x2(f[0], f[1]);
+                u.y = pack_bf16x2(f[2], f[3]);
+                u.z = pack_bf16x2(f[4], f[5]);
+                u.w = pack_bf16x2(f[6], f[7]);
+                *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + off + n) = u;
+              }
+            } else {
+              // ragged N tail (e.g. conv_out, N = 4): scalar path
+              for (int i = 0; i < 8 && n + i < p.N; ++i) {
+                float x = f[i];
+                if (p.bias) x += p.bias[n + i];
+                if (rv) x += __bfloat162float(rv[n + i]);
+                if (p.residual) x += __bfloat162float(p.residual[off + n + i]);
+                if (p.act == 1) x = silu_f(x);
+                if (p.out_fp32) {
+                  if (p.round_bf16) x = __bfloat162float(__float2bfloat16_rn(x));
+                  reinterpret_cast<float*>(p.out)[off + n + i] = x;
+                } else {
+                  reinterpret_cast<bf16*>(p.out)[off + n + i] = __float2bfloat16_rn(x);
+                }
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// LoRA weight gradient: out[ch, r] += alpha * sum_tokens P[tok(+tap), ch] * Q[tok, r]
+// ------------------------------------------------------------------------------------------
+struct alignas(64) WgradParams {
+  CUtensorMap p_map;
+  CUtensorMap q_map;
+  int lin, geoW, geoHW;
+  int M, Cp, q_c0;
+  int num_taps;
+  int dw[9], dh[9];
+  long long tap_off[9];
+  int ksplit, kblocks_total;
+  float* out;
+  long long os_row, os_col;
+  float alpha;
+};
+
+constexpr int kWgStages = 4;
+constexpr int kWgStageBytes = 3 * kATileBytes;  // P: 2 x (128 tok x 64 ch), Q: 128 tok x 64 r
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+pcm_wgrad_kernel(const __grid_constant__ WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  __shared__ __align__(8) uint64_t full_bar[kWgStages];
+  __shared__ __align__(8) uint64_t empty_bar[kWgStages];
+  __shared__ __align__(8) uint64_t tfull_bar;
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int ch0 = blockIdx.x * 128;
+  const int tap = blockIdx.y;
+  const int per = (p.kblocks_total + p.ksplit - 1) / p.ksplit;
+  const int kb_begin = blockIdx.z * per;
+  const int kb_end = min(p.kblocks_total, kb_begin + per);
+  const int nkb = kb_end - kb_begin;
+  if (nkb <= 0) return;  // uniform per CTA
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.p_map);
+    tma_prefetch_desc(&p.q_map);
+    for (int i = 0; i < kWgStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(&tfull_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_base_smem, 64);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        const int m0 = kb * 128;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&full_bar[stage], kWgStageBytes);
+        uint8_t* sp = smem + stage * kWgStageBytes;
+        uint8_t* sq = sp + 2 * kATileBytes;
+        if (p.lin) {
+          tma_load_4d(sp, &p.p_map, &full_bar[stage], ch0, m0, 0, 0);
+          tma_load_4d(sp + kATileBytes, &p.p_map, &full_bar[stage], ch0 + 64, m0, 0, 0);
+          tma_load_4d(sq, &p.q_map, &full_bar[stage], p.q_c0, m0, 0, 0);
+        } else {
+          const int b0 = m0 / p.geoHW;
+          const int h0 = (m0 - b0 * p.geoHW) / p.geoW;
+          tma_load_4d(sp, &p.p_map, &full_bar[stage], ch0, p.dw[tap], h0 + p.dh[tap], b0);
+          tma_load_4d(sp + kATileBytes, &p.p_map, &full_bar[stage], ch0 + 64, p.dw[tap],
+                      h0 + p.dh[tap], b0);
+          tma_load_4d(sq, &p.q_map, &full_bar[stage], p.q_c0, 0, h0, b0);
+        }
+        if (++stage == kWgStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, 64, 1, 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int i = 0; i < nkb; ++i) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t p_addr = smem_u32(smem + stage * kWgStageBytes);
+        const uint32_t q_addr = p_addr + 2 * kATileBytes;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {  // 16 tokens per UMMA
+          const uint64_t ad = umma_desc_sw128(p_addr + k * 2048, kATileBytes, 1024);
+          const uint64_t bd = umma_desc_sw128(q_addr + k * 2048, kATileBytes, 1024);
+          umma_f16(tmem_base, ad, bd, idesc, (i | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);
+        if (++stage == kWgStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma_commit(&tfull_bar);
+    }
+  } else {
+    const int q = warp & 3;
+    const int ch = ch0 + q * 32 + lane;
+    mbar_wait(&tfull_bar, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    float* o = p.out + p.tap_off[tap] + static_cast<long long>(ch) * p.os_row;
+    for (int j = 0; j < 64; j += 32) {
+      uint32_t v[32];
+      tmem_ld_32x32(taddr + j, v);
+      tmem_ld_wait();
+      if (ch < p.Cp) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          atomicAdd(o + static_cast<long long>(j + i) * p.os_col, __uint_as_float(v[i]) * p.alpha);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 64);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static int encode_asrc(CUtensorMap* map, const pcm_asrc& a, int lin, int geoW, int geoH,
+                       int box_c = 64) {
+  cuuint64_t dims[4];
+  cuuint64_t strides[3];
+  cuuint32_t box[4];
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  if (lin) {
+    // [rows = a.W, C] matrix; box = 64 x 128 rows
+    dims[0] = a.C; dims[1] = a.W; dims[2] = 1; dims[3] = 1;
+    strides[0] = a.sW * 2;
+    strides[1] = static_cast<cuuint64_t>(a.sW) * 2 * a.W;
+    strides[2] = strides[1];
+    box[0] = box_c; box[1] = 128; box[2] = 1; box[3] = 1;
+  } else {
+    dims[0] = a.C; dims[1] = a.W; dims[2] = a.H; dims[3] = a.B;
+    strides[0] = a.sW * 2; strides[1] = a.sH * 2; strides[2] = a.sB * 2;
+    const int bw = geoW;
+    if (bw > 128 || 128 % bw != 0) return set_error("conv geometry: W must divide 128");
+    int bh = 128 / bw;
+    if (bh > geoH) bh = geoH;
+    int bb = 128 / (bw * bh);
+    if (bw * bh * bb != 128) return set_error("conv geometry: H*W must divide or be divisible by 128");
+    box[0] = box_c; box[1] = bw; box[2] = bh; box[3] = bb;
+  }
+  return encode_tmap(map, a.ptr, 4, dims, strides, box, estr);
+}
+
+static int launch_gemm(const pcm_gemm_desc* d, cudaStream_t stream) {
+  if (d->block_n < 32 || d->block_n > 256 || (d->block_n % 32) != 0)
+    return set_error("pcm_gemm: block_n must be a multiple of 32 in [32, 256]");
+  if (d->num_a < 1 || d->num_a > PCM_MAX_ASRC || d->num_b < 1 || d->num_b > PCM_MAX_BSRC ||
+      d->num_prog < 1 || d->num_prog > PCM_MAX_PROG)
+    return set_error("pcm_gemm: bad source / program counts");
+  static GemmParams p;  // host staging (single host thread per rank)
+  memset(&p, 0, sizeof(p));
+  for (int i = 0; i < PCM_MAX_ASRC; ++i) {
+    const pcm_asrc& a = d->a[i < d->num_a ? i : 0];
+    if (int rc = encode_asrc(&p.a_maps[i], a, d->lin, d->geoW, d->geoH)) return rc;
+  }
+  for (int i = 0; i < PCM_MAX_BSRC; ++i) {
+    const pcm_bsrc& b = d->b[i < d->num_b ? i : 0];
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(b.K), static_cast<cuuint64_t>(b.N)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(b.ld) * 2};
+    cuuint32_t box[2] = {64, static_cast<cuuint32_t>(d->block_n)};
+    cuuint32_t estr[2] = {1, 1};
+    if (int rc = encode_tmap(&p.b_maps[i], b.ptr, 2, dims, strides, box, estr)) return rc;
+  }
+  int nkb = 0;
+  for (int e = 0; e < d->num_prog; ++e) {
+    const pcm_kentry& k = d->prog[e];
+    if (k.a_src < 0 || k.a_src >= d->num_a || k.b_src < 0 || k.b_src >= d->num_b || k.nchunks < 1)
+      return set_error("pcm_gemm: bad K program entry");
+    p.prog[e] = KEntry{k.a_src, k.b_src, k.dw, k.dh, k.nchunks, k.a_c0, k.b_k0, 0};
+    nkb += k.nchunks;
+  }
+  p.num_prog = d->num_prog;
+  p.lin = d->lin;
+  p.M = d->M;
+  p.N = d->N;
+  p.geoW = d->lin ? 1 : d->geoW;
+  p.geoHW = d->lin ? 1 : d->geoW * d->geoH;
+  p.block_n = d->block_n;
+  p.tiles_m = (d->M + 127) / 128;
+  p.tiles_n = (d->N + d->block_n - 1) / d->block_n;
+  p.num_kblocks = nkb;
+  const int stage_bytes = kATileBytes + d->block_n * 128;
+  int S = (200 * 1024) / stage_bytes;
+  if (S > kMaxStages) S = kMaxStages;
+  if (S < 2) return set_error("pcm_gemm: tile too large for shared memory");
+  p.num_stages = S;
+  p.out = d->out;
+  p.bias = d->bias;
+  p.rowvec = reinterpret_cast<const bf16*>(d->rowvec);
+  p.residual = reinterpret_cast<const bf16*>(d->residual);
+  p.osW = d->osW; p.osH = d->osH; p.osB = d->osB;
+  p.rowvec_ld = d->rowvec_ld;
+  p.epiW = d->epiW > 0 ? d->epiW : 1;
+  p.epiHW = d->epiHW > 0 ? d->epiHW : 1;
+  p.out_fp32 = d->out_fp32;
+  p.round_bf16 = d->round_bf16;
+  p.alpha = d->alpha;
+  p.act = d->act;
+
+  const size_t smem = static_cast<size_t>(S) * stage_bytes + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(pcm_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  227 * 1024));
+    attr_set = true;
+  }
+  const int tiles = p.tiles_m * p.tiles_n;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  pcm_gemm_kernel<<<grid, kGemmThreads, smem, stream>>>(p);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+static int launch_wgrad(const pcm_wgrad_desc* d, cudaStream_t stream) {
+  static WgradParams p;
+  memset(&p, 0, sizeof(p));
+  if (int rc = encode_asrc(&p.p_map, d->p, d->lin, d->geoW, d->geoH)) return rc;
+  if (int rc = encode_asrc(&p.q_map, d->q, d->lin, d->geoW, d->geoH)) return rc;
+  if (d->num_taps < 1 || d->num_taps > 9) return set_error("pcm_wgrad: bad tap count");
+  p.lin = d->lin;
+  p.geoW = d->lin ? 1 : d->geoW;
+  p.geoHW = d->lin ? 1 : d->geoW * d->geoH;
+  p.M = d->M;
+  p.Cp = d->p.C;
+  p.q_c0 = d->q_c0;
+  p.num_taps = d->num_taps;
+  for (int t = 0; t < d->num_taps; ++t) {
+    p.dw[t] = d->dw[t];
+    p.dh[t] = d->dh[t];
+    p.tap_off[t] = d->tap_off[t];
+  }
+  p.kblocks_total = (d->M + 127) / 128;
+  const int ch_tiles = (p.Cp + 127) / 128;
+  int ks = d->ksplit;
+  if (ks <= 0) {
+    // aim for ~2 waves of CTAs, at least 4 token blocks per CTA
+    ks = (2 * num_sms() + ch_tiles * d->num_taps - 1) / (ch_tiles * d->num_taps);
+    const int max_ks = (p.kblocks_total + 3) / 4;
+    if (ks > max_ks) ks = max_ks;
+    if (ks < 1) ks = 1;
+  }
+  if (ks > p.kblocks_total) ks = p.kblocks_total;
+  p.ksplit = ks;
+  p.out = d->out;
+  p.os_row = d->os_row;
+  p.os_col = d->os_col;
+  p.alpha = d->alpha;
+  const size_t smem = static_cast<size_t>(kWgStages) * kWgStageBytes + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(pcm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  227 * 1024));
+    attr_set = true;
+  }
+  dim3 grid(ch_tiles, d->num_taps, ks);
+  pcm_wgrad_kernel<<<grid, kGemmThreads, smem, stream>>>(p);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace pcm
+
+extern "C" int pcm_gemm(const pcm_gemm_desc* d, void* stream) {
+  return pcm::launch_gemm(d, reinterpret_cast<cudaStream_t>(stream));
+}
+extern "C" int pcm_wgrad(const pcm_wgrad_desc* d, void* stream) {
+  return pcm::launch_wgrad(d, reinterpret_cast<cudaStream_t>(stream));
+}

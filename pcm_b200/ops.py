@@ -1,0 +1,134 @@
+"""Thin Python wrappers over the C ABI (include/pcm_b200.h): torch tensors in, raw device pointers
+across the boundary, work enqueued on torch's current CUDA stream.  No compute happens in Python.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+BF16 = torch.bfloat16
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def asrc_nhwc(t):
+    """A-operand source from a bf16 [B, H, W, C] tensor (may be a strided view; C contiguous)."""
+    assert t.dtype == BF16 and t.dim() == 4 and t.stride(3) == 1, (t.dtype, t.shape, t.stride())
+    B, H, W, Cc = t.shape
+    return L.ASrc(t.data_ptr(), Cc, W, H, B, t.stride(2), t.stride(1), t.stride(0))
+
+
+def asrc_mat(t):
+    """A-operand source from a bf16 [M, C] matrix (row stride arbitrary, C contiguous)."""
+    assert t.dtype == BF16 and t.dim() == 2 and t.stride(1) == 1, (t.dtype, t.shape, t.stride())
+    M, Cc = t.shape
+    return L.ASrc(t.data_ptr(), Cc, M, 1, 1, t.stride(0), t.stride(0) * M, t.stride(0) * M)
+
+
+def bsrc(w):
+    """B-operand source from bf16 weights [N, K] (K contiguous)."""
+    assert w.dtype == BF16 and w.dim() == 2 and w.stride(1) == 1, (w.dtype, w.shape, w.stride())
+    return L.BSrc(w.data_ptr(), w.shape[1], w.shape[0], w.stride(0))
+
+
+_NUM_SMS = None
+
+
+def num_sms():
+    global _NUM_SMS
+    if _NUM_SMS is None:
+        _NUM_SMS = L.lib().pcm_num_sms()
+    return _NUM_SMS
+
+
+def pick_block_n(M, N):
+    """N tile (multiple of 32, <= 256) minimising waves x tile width on the persistent grid."""
+    tiles_m = (M + 127) // 128
+    sms = num_sms()
+    best, best_cost = None, None
+    for bn in (256, 224, 192, 160, 128, 96, 64, 32):
+        if bn > 32 and bn - 32 >= N:
+            continue
+        tiles = tiles_m * ((N + bn - 1) // bn)
+        waves = (tiles + sms - 1) // sms
+        cost = waves * (bn + 24)  # +24: per-tile fixed cost (epilogue drain, pipeline fill)
+        if best_cost is None or cost < best_cost:
+            best, best_cost = bn, cost
+    return best
+
+
+def gemm(a_srcs, b_srcs, prog, *, lin, M, N, out, geo=(1, 1), bias=None, rowvec=None,
+         residual=None, out_strides=None, epi=None, alpha=1.0, act=0, round_bf16=False,
+         block_n=None):
+    """Launch the tcgen05 implicit GEMM.  prog: list of (a_src, b_src, dw, dh, nchunks, a_c0, b_k0).
+
+    out: bf16 or fp32 tensor; rows are addressed as b*osB + h*osH + w*osW with (osW, osH, osB) =
+    out_strides (default: dense [M, ld] with ld = out.stride(-2))."""
+    d = L.GemmDesc()
+    for i, a in enumerate(a_srcs):
+        d.a[i] = a
+    for i, b in enumerate(b_srcs):
+        d.b[i] = b
+    for i, e in enumerate(prog):
+        d.prog[i] = L.KEntry(*e, 0)
+    d.num_a, d.num_b, d.num_prog = len(a_srcs), len(b_srcs), len(prog)
+    d.lin, d.M, d.N = int(lin), M, N
+    d.geoW, d.geoH = geo
+    d.block_n = block_n or pick_block_n(M, N)
+    d.out = out.data_ptr()
+    d.out_fp32 = int(out.dtype == torch.float32)
+    assert out.dtype in (torch.float32, BF16)
+    d.round_bf16 = int(round_bf16)
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() >= N
+        d.bias = bias.data_ptr()
+    if rowvec is not None:
+        assert rowvec.dtype == BF16 and rowvec.stride(-1) == 1
+        d.rowvec = rowvec.data_ptr()
+        d.rowvec_ld = rowvec.stride(0)
+    if residual is not None:
+        assert residual.dtype == BF16
+        d.residual = residual.data_ptr()
+    if out_strides is None:
+        ld = out.stride(-2)
+        if lin:
+            out_strides, epi = (ld, 0, 0), (1 << 30, 1 << 30)
+        else:
+            W, H = geo
+            out_strides, epi = (ld, ld * W, ld * W * H), (W, W * H)
+    d.osW, d.osH, d.osB = out_strides
+    d.epiW, d.epiHW = epi
+    d.alpha = alpha
+    d.act = act
+    L.check(L.lib().pcm_gemm(C.byref(d), _stream()), "pcm_gemm")
+    return out
+
+
+TAPS3 = [(kw - 1, kh - 1) for kh in range(3) for kw in range(3)]  # (dw, dh), tap = kh*3 + kw
+
+
+def wgrad(p_src, q_src, out, *, lin, M, geo=(1, 1), taps=((0, 0),), tap_off=(0,), os_row, os_col,
+          alpha=1.0, q_c0=0, ksplit=0):
+    """out[tap_off[t] + ch*os_row + r*os_col] += alpha * sum_m P[m(+tap t), ch] * Q[m, q_c0 + r]."""
+    assert out.dtype == torch.float32
+    d = L.WgradDesc()
+    d.p, d.q = p_src, q_src
+    d.q_c0, d.lin, d.M = q_c0, int(lin), M
+    d.geoW, d.geoH = geo
+    d.num_taps = len(taps)
+    for i, (dw, dh) in enumerate(taps):
+        d.dw[i], d.dh[i] = dw, dh
+        d.tap_off[i] = tap_off[i]
+    d.out = out.data_ptr()
+    d.os_row, d.os_col = os_row, os_col
+    d.ksplit = ksplit
+    d.alpha = alpha
+    L.check(L.lib().pcm_wgrad(C.byref(d), _stream()), "pcm_wgrad")
+    return out
