@@ -493,7 +493,7 @@ static int launch_gemm(const pcm_gemm_desc* d, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
     CUDA_TRY(cudaFuncSetAttribute(pcm_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  227 * 1024));
+                                  220 * 1024));
     attr_set = true;
   }
   const int tiles = p.tiles_m * p.tiles_n;
@@ -541,7 +541,7 @@ static int launch_wgrad(const pcm_wgrad_desc* d, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
     CUDA_TRY(cudaFuncSetAttribute(pcm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  227 * 1024));
+                                  220 * 1024));
     attr_set = true;
   }
   dim3 grid(ch_tiles, d->num_taps, ks);
