@@ -93,6 +93,79 @@ int pcm_num_sms(void);
 int pcm_gemm(const pcm_gemm_desc* d, void* stream);
 int pcm_wgrad(const pcm_wgrad_desc* d, void* stream);
 
+/* ---- GroupNorm(+SiLU) / LayerNorm (NHWC bf16; fp32 statistics) ----------------------------
+ * Replace ATen group_norm/layer_norm/silu inside diffusers ResnetBlock2D / Transformer2DModel /
+ * BasicTransformerBlock (T15:1192-1198, 1219-1244, 1263-1268) and their backward (T15:1296).
+ * x2/C2 (may be NULL/0) is the second half of a channel concat (up-block skip connections).
+ * stats: [B, G, 2] (sum, sumsq) written by fwd, consumed by bwd; red: [B, G, 2] scratch. */
+int pcm_groupnorm_fwd(const void* x1, const void* x2, int C1, int C2, int B, int HW, int G,
+                      const float* gamma, const float* beta, float eps, int silu, void* out,
+                      float* stats, void* stream);
+int pcm_groupnorm_bwd(const void* dy, const void* x1, const void* x2, int C1, int C2, int B, int HW,
+                      int G, const float* gamma, const float* beta, float eps, int silu,
+                      const float* stats, float* red, const void* add, void* dx1, void* dx2,
+                      void* stream);
+/* stats: [M, 2] (mean, rstd) */
+int pcm_layernorm_fwd(const void* x, int M, int C, const float* gamma, const float* beta, float eps,
+                      void* out, float* stats, void* stream);
+int pcm_layernorm_bwd(const void* dy, const void* x, int M, int C, const float* gamma,
+                      const float* stats, const void* add, void* dx, void* stream);
+
+/* ---- attention (flash style; q [B,Sq,H*D], k/v [B,Skv,H*D], row strides ld*) -------------
+ * Replaces the xformers / SDPA attention processor enabled at T15:947-961.
+ * lse, delta: [B, H, Sq] fp32. */
+int pcm_attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int B, int H,
+                 int Sq, int Skv, int D, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo,
+                 float scale, void* stream);
+int pcm_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout,
+                 const float* lse, float* delta, void* dq, void* dk, void* dv, int B, int H, int Sq,
+                 int Skv, int D, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, float scale,
+                 void* stream);
+
+/* ---- UNet glue (GEGLU, Upsample2D nearest, 4-channel edge convs, timestep sinusoid, ...) -- */
+int pcm_geglu_fwd(const void* u, int64_t M, int F, void* out, void* stream);
+int pcm_geglu_bwd(const void* dgg, const void* u, int64_t M, int F, void* du, void* stream);
+int pcm_upsample2x_fwd(const void* in, int B, int H, int W, int C, void* out, void* stream);
+int pcm_upsample2x_bwd(const void* dout, int B, int H, int W, int C, void* din, void* stream);
+/* in: fp32 [B,H,W,4]; w: bf16 [C][3][3][4]; sgn=+1 conv_in forward, -1 conv_out input gradient */
+int pcm_conv3x3_c4(const float* in, int B, int H, int W, int C, const void* w, const float* bias,
+                   int sgn, int round_in, void* out, void* stream);
+int pcm_timestep_embed(const int64_t* t, int B, int C, void* out, void* stream);
+int pcm_colsum(const void* x, int B, int HW, int C, void* out, void* stream);
+int pcm_add_bf16(const void* a, const void* b, int64_t n, void* out, void* stream);
+
+/* ---- PCM solver arithmetic (fused; fp32 latents, batch outermost, `per` elements/sample) ---
+ * coef: [B, 16] doubles (internal layout, see csrc/pcm_ops.cu). */
+/* T15:1143-1185 + DDIMSolver tables T15:289-303 + phase start T15:321-341 + c_skip T15:250-259 */
+int pcm_prepare(const float* alphas_cumprod, int num_train, int num_ddim, const int64_t* inf_idx,
+                int multiphase, const int64_t* index, const float* w, int B, int bf16_mode,
+                double* coef, int64_t* start_t, int64_t* t, int64_t* end_t, void* stream);
+/* DDPMScheduler.add_noise, S15:500-524 (T15:1178) */
+int pcm_add_noise(const float* x, const float* noise, const double* coef, int64_t per, int B,
+                  int bf16_mode, float* out, void* stream);
+/* predicted_origin x2 + CFG mix + DDIMSolver.ddim_step, T15:1224-1258 */
+int pcm_teacher_step(const float* eps_c, const float* eps_u, const float* noisy, const double* coef,
+                     int64_t per, int B, float* x_prev, void* stream);
+/* T15:1200-1212 + 1269-1293: loss (0 = huber, 1 = l2), d loss / d eps_student, optional dumps */
+int pcm_loss(const float* eps_s, const float* eps_t, const float* noisy, const float* x_prev,
+             const double* coef, int64_t per, int B, int loss_type, float huber_c, float* loss_out,
+             float* d_eps, float* model_pred, float* target, void* stream);
+/* DDPMScheduler.noise_travel, S15:526-554 */
+int pcm_noise_travel(const float* x, const float* noise, const float* alphas_cumprod,
+                     const int64_t* t_cur, const int64_t* t_tgt, int64_t per, int B, float* out,
+                     void* stream);
+
+/* ---- optimiser on the flat fp32 LoRA buffer (T15:1297-1301) ------------------------------- */
+int pcm_grad_sumsq(const float* g, int64_t n, double* out, void* stream);
+/* state: device float[2] = {lr, step}; step is incremented on device before the update */
+int pcm_adamw_clip(float* p, float* g, float* m, float* v, int64_t n, float* state, float beta1,
+                   float beta2, float eps, float weight_decay, float max_norm, float inv_world,
+                   const double* sumsq, int zero_grad, void* stream);
+/* table: num_entries x 9 int64 {a_off, b_off, a_fwd, sb_fwd, sb_t, a_t, cin|taps<<32, n|r<<32,
+ * work_begin}; writes bf16 operand copies A, s*B, (s*B)^T, A^T */
+int pcm_lora_refresh(const float* master, const void* table, int num_entries, int64_t total_work,
+                     float scale, void* opnd, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -67,13 +67,70 @@ def lib():
             fn = getattr(_lib, name)
             if name not in ("pcm_last_error",):
                 fn.restype = C.c_int
+            if name in ARGTYPES:
+                fn.argtypes = ARGTYPES[name]
     return _lib
 
 
 # every symbol include/pcm_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
-    "pcm_last_error", "pcm_version", "pcm_num_sms", "pcm_gemm", "pcm_wgrad",
+    "pcm_last_error",
+    "pcm_version",
+    "pcm_num_sms",
+    "pcm_gemm",
+    "pcm_wgrad",
+    "pcm_groupnorm_fwd",
+    "pcm_groupnorm_bwd",
+    "pcm_layernorm_fwd",
+    "pcm_layernorm_bwd",
+    "pcm_attn_fwd",
+    "pcm_attn_bwd",
+    "pcm_geglu_fwd",
+    "pcm_geglu_bwd",
+    "pcm_upsample2x_fwd",
+    "pcm_upsample2x_bwd",
+    "pcm_conv3x3_c4",
+    "pcm_timestep_embed",
+    "pcm_colsum",
+    "pcm_add_bf16",
+    "pcm_prepare",
+    "pcm_add_noise",
+    "pcm_teacher_step",
+    "pcm_loss",
+    "pcm_noise_travel",
+    "pcm_grad_sumsq",
+    "pcm_adamw_clip",
+    "pcm_lora_refresh",
 ]
+
+
+P, I, L64, F = C.c_void_p, C.c_int, C.c_int64, C.c_float
+ARGTYPES = {
+    "pcm_gemm": [P, P],
+    "pcm_wgrad": [P, P],
+    "pcm_groupnorm_fwd": [P, P, I, I, I, I, I, P, P, F, I, P, P, P],
+    "pcm_groupnorm_bwd": [P, P, P, I, I, I, I, I, P, P, F, I, P, P, P, P, P, P],
+    "pcm_layernorm_fwd": [P, I, I, P, P, F, P, P, P],
+    "pcm_layernorm_bwd": [P, P, I, I, P, P, P, P, P],
+    "pcm_attn_fwd": [P, P, P, P, P, I, I, I, I, I, L64, L64, L64, L64, F, P],
+    "pcm_attn_bwd": [P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, L64, L64, L64, L64, F, P],
+    "pcm_geglu_fwd": [P, L64, I, P, P],
+    "pcm_geglu_bwd": [P, P, L64, I, P, P],
+    "pcm_upsample2x_fwd": [P, I, I, I, I, P, P],
+    "pcm_upsample2x_bwd": [P, I, I, I, I, P, P],
+    "pcm_conv3x3_c4": [P, I, I, I, I, P, P, I, I, P, P],
+    "pcm_timestep_embed": [P, I, I, P, P],
+    "pcm_colsum": [P, I, I, I, P, P],
+    "pcm_add_bf16": [P, P, L64, P, P],
+    "pcm_prepare": [P, I, I, P, I, P, P, I, I, P, P, P, P, P],
+    "pcm_add_noise": [P, P, P, L64, I, I, P, P],
+    "pcm_teacher_step": [P, P, P, P, L64, I, P, P],
+    "pcm_loss": [P, P, P, P, P, L64, I, I, F, P, P, P, P, P],
+    "pcm_noise_travel": [P, P, P, P, P, L64, I, P, P],
+    "pcm_grad_sumsq": [P, L64, P, P],
+    "pcm_adamw_clip": [P, P, P, P, L64, P, F, F, F, F, F, F, P, I, P],
+    "pcm_lora_refresh": [P, P, I, L64, F, P, P],
+}
 
 
 class PcmError(RuntimeError):

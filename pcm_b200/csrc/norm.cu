@@ -1,0 +1,475 @@
+// GroupNorm(+SiLU) and LayerNorm, forward and input-gradient, on NHWC bf16 activations.
+// HBM-bound kernels: 16-byte vector loads along the contiguous channel dimension, fp32 statistics,
+// warp/shared-memory reductions, one bf16 rounding at the output.
+//
+// Replaces the ATen group_norm / layer_norm / silu launches inside diffusers' ResnetBlock2D,
+// Transformer2DModel and BasicTransformerBlock (called from train_pcm_lora_sd15.py:1192-1198,
+// 1219-1244, 1263-1268) and their autograd backward (:1296).  GroupNorm reads an optional second
+// source so the up-block skip concat torch.cat([h, res], dim=1) is never materialised twice.
+#include "common.cuh"
+#include "host_common.h"
+#include "../../include/pcm_b200.h"
+
+namespace pcm {
+
+// ------------------------------------------------------------------------------------------
+// GroupNorm statistics: stats[b, g] = (sum, sumsq) over HW x (C/G) elements
+// ------------------------------------------------------------------------------------------
+constexpr int kGnMaxC = 2560;
+
+__device__ __forceinline__ const bf16* gn_src(const bf16* x1, const bf16* x2, int C1, int C2,
+                                              long long pix, int c) {
+  return c < C1 ? x1 + pix * C1 + c : x2 + pix * C2 + (c - C1);
+}
+
+__global__ void gn_stats_kernel(const bf16* __restrict__ x1, const bf16* __restrict__ x2, int C1,
+                                int C2, int HW, int G, int pix_per_block,
+                                float* __restrict__ stats) {
+  __shared__ float s_sum[kGnMaxC];
+  __shared__ float s_sq[kGnMaxC];
+  const int C = C1 + C2;
+  const int b = blockIdx.y;
+  const int nvec = C >> 3;
+  const int tx = threadIdx.x % nvec, ty = threadIdx.x / nvec;
+  const int ny = blockDim.x / nvec;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    s_sum[i] = 0.f;
+    s_sq[i] = 0.f;
+  }
+  __syncthreads();
+  const int p0 = blockIdx.x * pix_per_block;
+  const int p1 = min(HW, p0 + pix_per_block);
+  float a[8], q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = q[i] = 0.f;
+  if (ty < ny) {
+    const int c = tx * 8;
+    for (int p = p0 + ty; p < p1; p += ny) {
+      const long long pix = static_cast<long long>(b) * HW + p;
+      const uint4 u = *reinterpret_cast<const uint4*>(gn_src(x1, x2, C1, C2, pix, c));
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = unpack_bf16x2(w[i]);
+        a[2 * i] += f.x; q[2 * i] += f.x * f.x;
+        a[2 * i + 1] += f.y; q[2 * i + 1] += f.y * f.y;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      atomicAdd(&s_sum[c + i], a[i]);
+      atomicAdd(&s_sq[c + i], q[i]);
+    }
+  }
+  __syncthreads();
+  const int cpg = C / G;
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    float s = 0.f, ss = 0.f;
+    for (int i = 0; i < cpg; ++i) {
+      s += s_sum[g * cpg + i];
+      ss += s_sq[g * cpg + i];
+    }
+    atomicAdd(&stats[(b * G + g) * 2], s);
+    atomicAdd(&stats[(b * G + g) * 2 + 1], ss);
+  }
+}
+
+// out = [silu]( (x - mean) * rstd * gamma + beta ), bf16
+__global__ void gn_apply_kernel(const bf16* __restrict__ x1, const bf16* __restrict__ x2, int C1,
+                                int C2, int HW, int G, long long total_vec,
+                                const float* __restrict__ stats, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, float eps, int silu,
+                                bf16* __restrict__ out) {
+  const int C = C1 + C2;
+  const int nvec = C >> 3;
+  const int cpg = C / G;
+  const float inv_n = 1.f / (static_cast<float>(HW) * cpg);
+  for (long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; v < total_vec;
+       v += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long pix = v / nvec;
+    const int c = static_cast<int>(v - pix * nvec) * 8;
+    const int b = static_cast<int>(pix / HW);
+    const uint4 u = *reinterpret_cast<const uint4*>(gn_src(x1, x2, C1, C2, pix, c));
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    float f[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 t = unpack_bf16x2(w[i]);
+      f[2 * i] = t.x;
+      f[2 * i + 1] = t.y;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int g = (c + i) / cpg;
+      const float mean = stats[(b * G + g) * 2] * inv_n;
+      const float var = fmaxf(stats[(b * G + g) * 2 + 1] * inv_n - mean * mean, 0.f);
+      const float rstd = rsqrtf(var + eps);
+      float y = (f[i] - mean) * rstd * gamma[c + i] + beta[c + i];
+      if (silu) y = silu_f(y);
+      f[i] = y;
+    }
+    uint4 o;
+    o.x = pack_bf16x2(f[0], f[1]);
+    o.y = pack_bf16x2(f[2], f[3]);
+    o.z = pack_bf16x2(f[4], f[5]);
+    o.w = pack_bf16x2(f[6], f[7]);
+    *reinterpret_cast<uint4*>(out + pix * C + c) = o;
+  }
+}
+
+// backward reductions: red[b, g] = (sum gamma*dyh, sum gamma*dyh*xhat), dyh = dy * silu'(pre)
+__global__ void gn_bwd_stats_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x1,
+                                    const bf16* __restrict__ x2, int C1, int C2, int HW, int G,
+                                    int pix_per_block, const float* __restrict__ stats,
+                                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                                    float eps, int silu, float* __restrict__ red) {
+  __shared__ float s_a[kGnMaxC];
+  __shared__ float s_b[kGnMaxC];
+  const int C = C1 + C2;
+  const int b = blockIdx.y;
+  const int nvec = C >> 3;
+  const int tx = threadIdx.x % nvec, ty = threadIdx.x / nvec;
+  const int ny = blockDim.x / nvec;
+  const int cpg = C / G;
+  const float inv_n = 1.f / (static_cast<float>(HW) * cpg);
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    s_a[i] = 0.f;
+    s_b[i] = 0.f;
+  }
+  __syncthreads();
+  const int p0 = blockIdx.x * pix_per_block;
+  const int p1 = min(HW, p0 + pix_per_block);
+  if (ty < ny) {
+    const int c = tx * 8;
+    float mean[8], rstd[8], gm[8], bt[8], a[8], q[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int g = (c + i) / cpg;
+      mean[i] = stats[(b * G + g) * 2] * inv_n;
+      const float var = fmaxf(stats[(b * G + g) * 2 + 1] * inv_n - mean[i] * mean[i], 0.f);
+      rstd[i] = rsqrtf(var + eps);
+      gm[i] = gamma[c + i];
+      bt[i] = beta[c + i];
+      a[i] = q[i] = 0.f;
+    }
+    for (int p = p0 + ty; p < p1; p += ny) {
+      const long long pix = static_cast<long long>(b) * HW + p;
+      const uint4 u = *reinterpret_cast<const uint4*>(gn_src(x1, x2, C1, C2, pix, c));
+      const uint4 d = *reinterpret_cast<const uint4*>(dy + pix * C + c);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+      const uint32_t dw[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 xf = unpack_bf16x2(w[i]);
+        const float2 df = unpack_bf16x2(dw[i]);
+        const float xs[2] = {xf.x, xf.y}, ds[2] = {df.x, df.y};
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int k = 2 * i + j;
+          const float xh = (xs[j] - mean[k]) * rstd[k];
+          float g = ds[j];
+          if (silu) g *= dsilu_f(xh * gm[k] + bt[k]);
+          g *= gm[k];
+          a[k] += g;
+          q[k] += g * xh;
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      atomicAdd(&s_a[c + i], a[i]);
+      atomicAdd(&s_b[c + i], q[i]);
+    }
+  }
+  __syncthreads();
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    float s = 0.f, ss = 0.f;
+    for (int i = 0; i < cpg; ++i) {
+      s += s_a[g * cpg + i];
+      ss += s_b[g * cpg + i];
+    }
+    atomicAdd(&red[(b * G + g) * 2], s);
+    atomicAdd(&red[(b * G + g) * 2 + 1], ss);
+  }
+}
+
+// dx = rstd * (gamma*dyh - (s1 + xhat*s2)/n) (+ add); written to dx1 (first C1 channels) and
+// dx2 (remaining C2 channels).
+__global__ void gn_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x1,
+                                    const bf16* __restrict__ x2, int C1, int C2, int HW, int G,
+                                    long long total_vec, const float* __restrict__ stats,
+                                    const float* __restrict__ red, const float* __restrict__ gamma,
+                                    const float* __restrict__ beta, float eps, int silu,
+                                    const bf16* __restrict__ add, bf16* __restrict__ dx1,
+                                    bf16* __restrict__ dx2) {
+  const int C = C1 + C2;
+  const int nvec = C >> 3;
+  const int cpg = C / G;
+  const float inv_n = 1.f / (static_cast<float>(HW) * cpg);
+  for (long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; v < total_vec;
+       v += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long pix = v / nvec;
+    const int c = static_cast<int>(v - pix * nvec) * 8;
+    const int b = static_cast<int>(pix / HW);
+    const uint4 u = *reinterpret_cast<const uint4*>(gn_src(x1, x2, C1, C2, pix, c));
+    const uint4 d = *reinterpret_cast<const uint4*>(dy + pix * C + c);
+    uint4 ad = make_uint4(0, 0, 0, 0);
+    if (add) ad = *reinterpret_cast<const uint4*>(add + pix * C + c);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    const uint32_t dw[4] = {d.x, d.y, d.z, d.w};
+    const uint32_t aw[4] = {ad.x, ad.y, ad.z, ad.w};
+    float o[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 xf = unpack_bf16x2(w[i]);
+      const float2 df = unpack_bf16x2(dw[i]);
+      const float2 af = unpack_bf16x2(aw[i]);
+      const float xs[2] = {xf.x, xf.y}, ds[2] = {df.x, df.y}, as[2] = {af.x, af.y};
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int k = 2 * i + j;
+        const int g = (c + k) / cpg;
+        const float mean = stats[(b * G + g) * 2] * inv_n;
+        const float var = fmaxf(stats[(b * G + g) * 2 + 1] * inv_n - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + eps);
+        const float gmk = gamma[c + k];
+        const float xh = (xs[j] - mean) * rstd;
+        float gg = ds[j];
+        if (silu) gg *= dsilu_f(xh * gmk + beta[c + k]);
+        gg *= gmk;
+        const float s1 = red[(b * G + g) * 2] * inv_n;
+        const float s2 = red[(b * G + g) * 2 + 1] * inv_n;
+        o[k] = rstd * (gg - s1 - xh * s2) + as[j];
+      }
+    }
+    uint4 ov;
+    ov.x = pack_bf16x2(o[0], o[1]);
+    ov.y = pack_bf16x2(o[2], o[3]);
+    ov.z = pack_bf16x2(o[4], o[5]);
+    ov.w = pack_bf16x2(o[6], o[7]);
+    if (c < C1)
+      *reinterpret_cast<uint4*>(dx1 + pix * C1 + c) = ov;
+    else
+      *reinterpret_cast<uint4*>(dx2 + pix * C2 + (c - C1)) = ov;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm over the channel dimension, one warp per token row (C <= 1280, C % 8 == 0)
+// ------------------------------------------------------------------------------------------
+constexpr int kLnMaxVec = 5;  // per lane: C/8/32 <= 5
+
+__global__ void ln_fwd_kernel(const bf16* __restrict__ x, int M, int C,
+                              const float* __restrict__ gamma, const float* __restrict__ beta,
+                              float eps, bf16* __restrict__ out, float* __restrict__ stats) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= M) return;
+  const int nvec = C >> 3;
+  const bf16* row = x + static_cast<long long>(warp) * C;
+  float f[kLnMaxVec][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    const int v = lane + i * 32;
+    if (v < nvec) {
+      const uint4 u = *reinterpret_cast<const uint4*>(row + v * 8);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 t = unpack_bf16x2(w[j]);
+        f[i][2 * j] = t.x;
+        f[i][2 * j + 1] = t.y;
+        s += t.x + t.y;
+      }
+    }
+  }
+  const float mean = warp_sum(s) / C;
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    const int v = lane + i * 32;
+    if (v < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = f[i][j] - mean;
+        ss += d * d;
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(ss) / C + eps);
+  if (lane == 0 && stats) {
+    stats[warp * 2] = mean;
+    stats[warp * 2 + 1] = rstd;
+  }
+  bf16* orow = out + static_cast<long long>(warp) * C;
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    const int v = lane + i * 32;
+    if (v < nvec) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        o[j] = (f[i][j] - mean) * rstd * gamma[v * 8 + j] + beta[v * 8 + j];
+      uint4 u;
+      u.x = pack_bf16x2(o[0], o[1]);
+      u.y = pack_bf16x2(o[2], o[3]);
+      u.z = pack_bf16x2(o[4], o[5]);
+      u.w = pack_bf16x2(o[6], o[7]);
+      *reinterpret_cast<uint4*>(orow + v * 8) = u;
+    }
+  }
+}
+
+// dx = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat)) (+ add)
+__global__ void ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, int M, int C,
+                              const float* __restrict__ gamma, const float* __restrict__ stats,
+                              const bf16* __restrict__ add, bf16* __restrict__ dx) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= M) return;
+  const int nvec = C >> 3;
+  const long long base = static_cast<long long>(warp) * C;
+  const float mean = stats[warp * 2], rstd = stats[warp * 2 + 1];
+  float g[kLnMaxVec][8], xh[kLnMaxVec][8];
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    const int v = lane + i * 32;
+    if (v < nvec) {
+      const uint4 u = *reinterpret_cast<const uint4*>(x + base + v * 8);
+      const uint4 d = *reinterpret_cast<const uint4*>(dy + base + v * 8);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+      const uint32_t dw[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 xf = unpack_bf16x2(w[j]);
+        const float2 df = unpack_bf16x2(dw[j]);
+        xh[i][2 * j] = (xf.x - mean) * rstd;
+        xh[i][2 * j + 1] = (xf.y - mean) * rstd;
+        g[i][2 * j] = df.x * gamma[v * 8 + 2 * j];
+        g[i][2 * j + 1] = df.y * gamma[v * 8 + 2 * j + 1];
+        s1 += g[i][2 * j] + g[i][2 * j + 1];
+        s2 += g[i][2 * j] * xh[i][2 * j] + g[i][2 * j + 1] * xh[i][2 * j + 1];
+      }
+    }
+  }
+  s1 = warp_sum(s1) / C;
+  s2 = warp_sum(s2) / C;
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    const int v = lane + i * 32;
+    if (v < nvec) {
+      float o[8];
+      float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (add) {
+        const uint4 u = *reinterpret_cast<const uint4*>(add + base + v * 8);
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 t = unpack_bf16x2(w[j]);
+          a[2 * j] = t.x;
+          a[2 * j + 1] = t.y;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = rstd * (g[i][j] - s1 - xh[i][j] * s2) + a[j];
+      uint4 u;
+      u.x = pack_bf16x2(o[0], o[1]);
+      u.y = pack_bf16x2(o[2], o[3]);
+      u.z = pack_bf16x2(o[4], o[5]);
+      u.w = pack_bf16x2(o[6], o[7]);
+      *reinterpret_cast<uint4*>(dx + base + v * 8) = u;
+    }
+  }
+}
+
+static int gn_launch_cfg(int C, int HW, int B, int* threads, int* ppb, int* nblk) {
+  const int nvec = C / 8;
+  if (C % 8 != 0 || C > kGnMaxC || nvec > 1024) return set_error("groupnorm: unsupported C");
+  int ny = 512 / nvec;
+  if (ny < 1) ny = 1;
+  *threads = nvec * ny;
+  // ~4 waves of blocks over the chip
+  int target_blocks = (4 * num_sms() + B - 1) / B;
+  int p = (HW + target_blocks - 1) / target_blocks;
+  if (p < ny * 4) p = ny * 4;
+  *ppb = p;
+  *nblk = (HW + p - 1) / p;
+  return 0;
+}
+
+}  // namespace pcm
+
+using namespace pcm;
+
+extern "C" int pcm_groupnorm_fwd(const void* x1, const void* x2, int C1, int C2, int B, int HW,
+                                 int G, const float* gamma, const float* beta, float eps, int silu,
+                                 void* out, float* stats, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const int C = C1 + C2;
+  if (C % G != 0 || C1 % 8 != 0 || C2 % 8 != 0) return set_error("groupnorm: bad channel split");
+  int threads, ppb, nblk;
+  if (int rc = gn_launch_cfg(C, HW, B, &threads, &ppb, &nblk)) return rc;
+  CUDA_TRY(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * B * G, stream));
+  gn_stats_kernel<<<dim3(nblk, B), threads, 0, stream>>>(
+      reinterpret_cast<const bf16*>(x1), reinterpret_cast<const bf16*>(x2), C1, C2, HW, G, ppb,
+      stats);
+  const long long total_vec = static_cast<long long>(B) * HW * (C / 8);
+  int grid = static_cast<int>((total_vec + 255) / 256);
+  if (grid > num_sms() * 16) grid = num_sms() * 16;
+  gn_apply_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const bf16*>(x1),
+                                            reinterpret_cast<const bf16*>(x2), C1, C2, HW, G,
+                                            total_vec, stats, gamma, beta, eps, silu,
+                                            reinterpret_cast<bf16*>(out));
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int pcm_groupnorm_bwd(const void* dy, const void* x1, const void* x2, int C1, int C2,
+                                 int B, int HW, int G, const float* gamma, const float* beta,
+                                 float eps, int silu, const float* stats, float* red,
+                                 const void* add, void* dx1, void* dx2, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const int C = C1 + C2;
+  int threads, ppb, nblk;
+  if (int rc = gn_launch_cfg(C, HW, B, &threads, &ppb, &nblk)) return rc;
+  CUDA_TRY(cudaMemsetAsync(red, 0, sizeof(float) * 2 * B * G, stream));
+  gn_bwd_stats_kernel<<<dim3(nblk, B), threads, 0, stream>>>(
+      reinterpret_cast<const bf16*>(dy), reinterpret_cast<const bf16*>(x1),
+      reinterpret_cast<const bf16*>(x2), C1, C2, HW, G, ppb, stats, gamma, beta, eps, silu, red);
+  const long long total_vec = static_cast<long long>(B) * HW * (C / 8);
+  int grid = static_cast<int>((total_vec + 255) / 256);
+  if (grid > num_sms() * 16) grid = num_sms() * 16;
+  gn_bwd_apply_kernel<<<grid, 256, 0, stream>>>(
+      reinterpret_cast<const bf16*>(dy), reinterpret_cast<const bf16*>(x1),
+      reinterpret_cast<const bf16*>(x2), C1, C2, HW, G, total_vec, stats, red, gamma, beta, eps,
+      silu, reinterpret_cast<const bf16*>(add), reinterpret_cast<bf16*>(dx1),
+      reinterpret_cast<bf16*>(dx2));
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int pcm_layernorm_fwd(const void* x, int M, int C, const float* gamma,
+                                 const float* beta, float eps, void* out, float* stats,
+                                 void* stream_) {
+  if (C % 8 != 0 || C > kLnMaxVec * 256) return set_error("layernorm: unsupported C");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const int wpb = 8;
+  ln_fwd_kernel<<<(M + wpb - 1) / wpb, wpb * 32, 0, stream>>>(
+      reinterpret_cast<const bf16*>(x), M, C, gamma, beta, eps, reinterpret_cast<bf16*>(out), stats);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int pcm_layernorm_bwd(const void* dy, const void* x, int M, int C, const float* gamma,
+                                 const float* stats, const void* add, void* dx, void* stream_) {
+  if (C % 8 != 0 || C > kLnMaxVec * 256) return set_error("layernorm: unsupported C");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const int wpb = 8;
+  ln_bwd_kernel<<<(M + wpb - 1) / wpb, wpb * 32, 0, stream>>>(
+      reinterpret_cast<const bf16*>(dy), reinterpret_cast<const bf16*>(x), M, C, gamma, stats,
+      reinterpret_cast<const bf16*>(add), reinterpret_cast<bf16*>(dx));
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}

@@ -132,3 +132,101 @@ def wgrad(p_src, q_src, out, *, lin, M, geo=(1, 1), taps=((0, 0),), tap_off=(0,)
     d.alpha = alpha
     L.check(L.lib().pcm_wgrad(C.byref(d), _stream()), "pcm_wgrad")
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# normalisation / attention / glue / PCM math / optimiser wrappers
+# ---------------------------------------------------------------------------------------------
+def _p(t):
+    return t.data_ptr() if t is not None else None
+
+
+def _call(name, *args):
+    L.check(getattr(L.lib(), name)(*args, torch.cuda.current_stream().cuda_stream), name)
+
+
+def groupnorm_fwd(x1, x2, gamma, beta, eps, silu, out, stats, B, HW, G=32):
+    C1 = x1.shape[-1]
+    C2 = x2.shape[-1] if x2 is not None else 0
+    _call("pcm_groupnorm_fwd", _p(x1), _p(x2), C1, C2, B, HW, G, _p(gamma), _p(beta), eps, int(silu),
+          _p(out), _p(stats))
+    return out
+
+
+def groupnorm_bwd(dy, x1, x2, gamma, beta, eps, silu, stats, red, add, dx1, dx2, B, HW, G=32):
+    C1 = x1.shape[-1]
+    C2 = x2.shape[-1] if x2 is not None else 0
+    _call("pcm_groupnorm_bwd", _p(dy), _p(x1), _p(x2), C1, C2, B, HW, G, _p(gamma), _p(beta), eps,
+          int(silu), _p(stats), _p(red), _p(add), _p(dx1), _p(dx2))
+
+
+def layernorm_fwd(x, gamma, beta, out, stats, eps=1e-5):
+    M, Cc = x.shape
+    _call("pcm_layernorm_fwd", _p(x), M, Cc, _p(gamma), _p(beta), eps, _p(out), _p(stats))
+    return out
+
+
+def layernorm_bwd(dy, x, gamma, stats, add, dx):
+    M, Cc = x.shape
+    _call("pcm_layernorm_bwd", _p(dy), _p(x), M, Cc, _p(gamma), _p(stats), _p(add), _p(dx))
+    return dx
+
+
+def attn_fwd(q, k, v, out, lse, B, H, Sq, Skv, D, scale):
+    """q/out: [B*Sq, >=H*D] views, k/v: [B*Skv, >=H*D] views (row stride = .stride(0))."""
+    _call("pcm_attn_fwd", _p(q), _p(k), _p(v), _p(out), _p(lse), B, H, Sq, Skv, D, q.stride(0),
+          k.stride(0), v.stride(0), out.stride(0), scale)
+    return out
+
+
+def attn_bwd(q, k, v, o, dout, lse, delta, dq, dk, dv, B, H, Sq, Skv, D, scale):
+    assert o.stride(0) == dout.stride(0) and dq.stride(0) == q.stride(0)
+    assert dk.stride(0) == k.stride(0) and dv.stride(0) == v.stride(0)
+    _call("pcm_attn_bwd", _p(q), _p(k), _p(v), _p(o), _p(dout), _p(lse), _p(delta), _p(dq), _p(dk),
+          _p(dv), B, H, Sq, Skv, D, q.stride(0), k.stride(0), v.stride(0), o.stride(0), scale)
+
+
+def geglu_fwd(u, out):
+    M, F2 = u.shape
+    _call("pcm_geglu_fwd", _p(u), M, F2 // 2, _p(out))
+    return out
+
+
+def geglu_bwd(dgg, u, du):
+    M, F2 = u.shape
+    _call("pcm_geglu_bwd", _p(dgg), _p(u), M, F2 // 2, _p(du))
+    return du
+
+
+def upsample2x_fwd(x, out):
+    B, H, W, Cc = x.shape
+    _call("pcm_upsample2x_fwd", _p(x), B, H, W, Cc, _p(out))
+    return out
+
+
+def upsample2x_bwd(dout, din):
+    B, H, W, Cc = din.shape
+    _call("pcm_upsample2x_bwd", _p(dout), B, H, W, Cc, _p(din))
+    return din
+
+
+def conv3x3_c4(x, w, bias, out, sgn=1, round_in=True):
+    B, H, W, four = x.shape
+    assert four == 4 and x.dtype == torch.float32
+    _call("pcm_conv3x3_c4", _p(x), B, H, W, out.shape[-1], _p(w), _p(bias), sgn, int(round_in), _p(out))
+    return out
+
+
+def timestep_embed(t, out):
+    _call("pcm_timestep_embed", _p(t), out.shape[0], out.shape[1], _p(out))
+    return out
+
+
+def colsum(x, out, B, HW):
+    _call("pcm_colsum", _p(x), B, HW, x.shape[-1], _p(out))
+    return out
+
+
+def add_bf16(a, b, out):
+    _call("pcm_add_bf16", _p(a), _p(b), a.numel(), _p(out))
+    return out
