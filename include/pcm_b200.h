@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-#define PCM_MAX_ASRC 4
+#define PCM_MAX_ASRC 6
 #define PCM_MAX_BSRC 2
 #define PCM_MAX_PROG 24
 

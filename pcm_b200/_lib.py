@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libpcm_b200.so")
 
-MAX_ASRC, MAX_BSRC, MAX_PROG = 4, 2, 24
+MAX_ASRC, MAX_BSRC, MAX_PROG = 6, 2, 24
 
 
 class ASrc(C.Structure):

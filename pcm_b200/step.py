@@ -1,0 +1,157 @@
+"""One PCM-LoRA distillation iteration on the B200 path: the body of the reference loop
+train_pcm_lora_sd15.py:1139-1301 (noise / phase bookkeeping, student forward, teacher CFG DDIM
+step, target forward, Huber loss, backward, gradient all-reduce, clip + AdamW) as a fixed sequence
+of C-ABI kernel launches, capturable in ONE CUDA graph (no host sync inside; `index`, `w`,
+timesteps, lr and the optimiser step counter live in device memory).
+"""
+import numpy as np
+import torch
+
+from . import ops
+from .config import UNetConfig
+from .unet import UNetB200
+
+BF16 = torch.bfloat16
+
+
+def sd15_alphas_cumprod(num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012):
+    """`scaled_linear` betas of the SD1.5 DDPMScheduler config (scheduling_ddpm_modified.py:211-215)."""
+    betas = torch.linspace(beta_start ** 0.5, beta_end ** 0.5, num_train_timesteps, dtype=torch.float32) ** 2
+    return torch.cumprod(1.0 - betas, dim=0)
+
+
+def inference_indices(num_ddim, multiphase):
+    """Phase start indices, np.floor(np.linspace(0, N, multiphase, endpoint=False))
+    (train_pcm_lora_sd15.py:1157-1160 / :322-325)."""
+    return np.floor(np.linspace(0, num_ddim, num=multiphase, endpoint=False)).astype(np.int64)
+
+
+class PCMTrainStep:
+    """State + one-iteration driver.  All tensors NHWC; latents fp32 [B, H, W, 4]."""
+
+    def __init__(self, cfg: UNetConfig, state_dict, device, *, batch, height, width, multiphase=4,
+                 num_ddim_timesteps=50, num_train_timesteps=1000, loss_type="huber", huber_c=1e-3,
+                 lr=5e-6, betas=(0.9, 0.999), adam_eps=1e-8, weight_decay=1e-2, max_grad_norm=1.0,
+                 apply_cfg_solver=True, bf16_mode=True, alphas_cumprod=None, process_group=None,
+                 keep_debug=False):
+        self.cfg, self.dev = cfg, device
+        self.B, self.H, self.W = batch, height, width
+        self.per = height * width * 4
+        self.unet = UNetB200(cfg, state_dict, device, need_backward=True, lora=True)
+        self.multiphase, self.num_ddim, self.num_train = multiphase, num_ddim_timesteps, num_train_timesteps
+        self.loss_type = 0 if loss_type == "huber" else 1
+        self.huber_c = huber_c
+        self.betas, self.adam_eps, self.wd, self.max_norm = betas, adam_eps, weight_decay, max_grad_norm
+        self.apply_cfg = apply_cfg_solver
+        self.bf16_mode = int(bf16_mode)
+        self.pg = process_group
+        self.world = 1 if process_group is None else torch.distributed.get_world_size(process_group)
+        acp = sd15_alphas_cumprod(num_train_timesteps) if alphas_cumprod is None else alphas_cumprod
+        self.acp = acp.float().to(device)
+        self.inf_idx = torch.from_numpy(inference_indices(num_ddim_timesteps, multiphase)).to(device)
+        f32 = dict(device=device, dtype=torch.float32)
+        i64 = dict(device=device, dtype=torch.int64)
+        B = batch
+        self.coef = torch.zeros(B, 16, device=device, dtype=torch.float64)
+        self.start_t, self.t, self.end_t = (torch.zeros(B, **i64) for _ in range(3))
+        self.noisy = torch.zeros(B, height, width, 4, **f32)
+        self.x_prev = torch.zeros_like(self.noisy)
+        self.d_eps = torch.zeros_like(self.noisy)
+        self.loss = torch.zeros(1, **f32)
+        self.model_pred = torch.zeros_like(self.noisy) if keep_debug else None
+        self.target = torch.zeros_like(self.noisy) if keep_debug else None
+        n = self.unet.lora_master.numel()
+        self.exp_avg = torch.zeros(n, **f32)
+        self.exp_avg_sq = torch.zeros(n, **f32)
+        self.opt_state = torch.tensor([lr, 0.0], **f32)  # lr, step
+        self.sumsq = torch.zeros(1, device=device, dtype=torch.float64)
+        self.debug = {} if keep_debug else None
+        # static input slots (graph replay copies into these)
+        self.in_latents = torch.zeros(B, height, width, 4, **f32)
+        self.in_noise = torch.zeros_like(self.in_latents)
+        self.in_index = torch.zeros(B, **i64)
+        self.in_w = torch.zeros(B, **f32)
+        self.in_prompt = torch.zeros(B * 77, cfg.cross_attention_dim, device=device, dtype=BF16)
+        self.in_uncond = torch.zeros_like(self.in_prompt)
+        self.graph = None
+
+    def set_lr(self, lr):
+        self.opt_state[0] = lr
+
+    # -- the iteration ------------------------------------------------------------------
+    def forward_backward(self):
+        """Everything up to (and including) the LoRA gradients, from the static input slots."""
+        u, B, per = self.unet, self.B, self.per
+        ops._call("pcm_prepare", self.acp.data_ptr(), self.num_train, self.num_ddim, self.inf_idx.data_ptr(),
+                  self.multiphase, self.in_index.data_ptr(), self.in_w.data_ptr(), B, self.bf16_mode,
+                  self.coef.data_ptr(), self.start_t.data_ptr(), self.t.data_ptr(), self.end_t.data_ptr())
+        ops._call("pcm_add_noise", self.in_latents.data_ptr(), self.in_noise.data_ptr(), self.coef.data_ptr(),
+                  per, B, self.bf16_mode, self.noisy.data_ptr())
+        eps_s = u.forward(self.noisy, self.start_t, self.in_prompt, lora=True, save=True)
+        eps_c = u.forward(self.noisy, self.start_t, self.in_prompt, lora=False)
+        eps_u = u.forward(self.noisy, self.start_t, self.in_uncond, lora=False) if self.apply_cfg else eps_c
+        ops._call("pcm_teacher_step", eps_c.data_ptr(), eps_u.data_ptr(), self.noisy.data_ptr(),
+                  self.coef.data_ptr(), per, B, self.x_prev.data_ptr())
+        eps_t = u.forward(self.x_prev, self.t, self.in_prompt, lora=True)
+        ops._call("pcm_loss", eps_s.data_ptr(), eps_t.data_ptr(), self.noisy.data_ptr(), self.x_prev.data_ptr(),
+                  self.coef.data_ptr(), per, B, self.loss_type, self.huber_c, self.loss.data_ptr(),
+                  self.d_eps.data_ptr(), ops._p(self.model_pred), ops._p(self.target))
+        if self.debug is not None:
+            self.debug.update(eps_student=eps_s, eps_cond=eps_c, eps_uncond=eps_u, eps_target=eps_t)
+        u.backward(self.d_eps)
+
+    def optimizer_step(self):
+        u = self.unet
+        g = u.lora_grad
+        if self.world > 1:
+            torch.distributed.all_reduce(g, group=self.pg)  # sum; the 1/world is folded into AdamW
+        ops._call("pcm_grad_sumsq", g.data_ptr(), g.numel(), self.sumsq.data_ptr())
+        ops._call("pcm_adamw_clip", u.lora_master.data_ptr(), g.data_ptr(), self.exp_avg.data_ptr(),
+                  self.exp_avg_sq.data_ptr(), g.numel(), self.opt_state.data_ptr(), self.betas[0],
+                  self.betas[1], self.adam_eps, self.wd, self.max_norm, 1.0 / self.world,
+                  self.sumsq.data_ptr(), 1)
+        u.refresh_lora()
+
+    def run_eager(self, optimizer=True):
+        self.forward_backward()
+        if optimizer:
+            self.optimizer_step()
+        return self.loss
+
+    def capture(self, warmup=2):
+        """Capture forward+backward+optimiser into one CUDA graph (after eager warm-up runs)."""
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        snap = (self.unet.lora_master.clone(), self.exp_avg.clone(), self.exp_avg_sq.clone(),
+                self.opt_state.clone())
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                self.run_eager()
+        torch.cuda.current_stream().wait_stream(s)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.run_eager()
+        # the warm-up / capture runs must not count as training steps
+        self.unet.lora_master.copy_(snap[0])
+        self.exp_avg.copy_(snap[1])
+        self.exp_avg_sq.copy_(snap[2])
+        self.opt_state.copy_(snap[3])
+        self.unet.lora_grad.zero_()
+        self.unet.refresh_lora()
+        return self.graph
+
+    def load_inputs(self, latents, noise, index, w, prompt, uncond, non_blocking=True):
+        """Copy one batch into the static slots (host pinned or device tensors, NHWC latents)."""
+        self.in_latents.copy_(latents, non_blocking=non_blocking)
+        self.in_noise.copy_(noise, non_blocking=non_blocking)
+        self.in_index.copy_(index, non_blocking=non_blocking)
+        self.in_w.copy_(w, non_blocking=non_blocking)
+        self.in_prompt.copy_(prompt.reshape(self.in_prompt.shape), non_blocking=non_blocking)
+        self.in_uncond.copy_(uncond.reshape(self.in_uncond.shape), non_blocking=non_blocking)
+
+    def step(self):
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self.run_eager()
+        return self.loss

@@ -1,0 +1,626 @@
+"""B200-native SD1.5 UNet (student / target with fused LoRA, frozen teacher) -- host orchestration.
+
+Python only sequences C-ABI kernel launches (pcm_b200.ops); every FLOP runs in libpcm_b200.so.
+Mirrors the call `unet(sample, timestep, encoder_hidden_states=...).sample` of diffusers'
+UNet2DConditionModel wrapped by peft (train_pcm_lora_sd15.py:1192-1198 student, :1219-1244
+teacher, :1263-1268 target) and its autograd backward (:1296), with:
+  * activations NHWC bf16, one rounding per materialised tensor (bf16 autocast semantics);
+  * LoRA unmerged: T = A(x) as a 64-wide GEMM, then s*B*T enters the base GEMM as one extra
+    64-wide K block (same TMEM accumulator), so `base(x) + B(A(x)) * scaling` is one kernel;
+  * skip concats never materialised (two K segments / two GroupNorm sources);
+  * backward = explicit tape: dgrad through every layer, wgrad for LoRA factors only.
+Parameters use diffusers state-dict names; LoRA factors live in ONE flat fp32 buffer
+(`lora_master`), their gradients in `lora_grad`.
+"""
+import torch
+
+from . import ops
+from .config import UNetConfig, is_lora_target, layer_table
+
+BF16 = torch.bfloat16
+TAPS3 = ops.TAPS3
+# stride-2 3x3 pad-1: kernel index -> (input parity, shift in the parity plane)
+_S2 = ((1, -1), (0, 0), (1, 0))
+
+
+class _Lora:
+    __slots__ = ("a_off", "b_off", "a_fwd", "sb_fwd", "sb_t", "a_t", "gA", "gB", "opnd_off")
+
+
+class _Layer:
+    __slots__ = ("name", "kind", "cin", "cout", "k", "w_fwd", "w_t", "bias", "gamma", "beta", "lora",
+                 "w_c4", "w_c4_t")
+
+
+class UNetB200:
+    def __init__(self, cfg: UNetConfig, state_dict, device, need_backward=True, lora=True):
+        self.cfg, self.dev = cfg, device
+        self.r = cfg.lora_rank
+        self.scale = cfg.lora_scale
+        self.layers = {}
+        self.has_lora = lora
+        tab = layer_table(cfg)
+        master, entries, opnd_total = [], [], 0
+        moff = 0
+        no_dgrad = ("attn2.to_k", "attn2.to_v", "time_emb_proj")
+        for name, kind, cin, cout, k in tab:
+            L = _Layer()
+            L.name, L.kind, L.cin, L.cout, L.k = name, kind, cin, cout, k
+            L.w_fwd = L.w_t = L.bias = L.gamma = L.beta = L.lora = L.w_c4 = L.w_c4_t = None
+            if kind in ("gn", "ln"):
+                L.gamma = state_dict[name + ".weight"].float().to(device)
+                L.beta = state_dict[name + ".bias"].float().to(device)
+                self.layers[name] = L
+                continue
+            W = state_dict[name + ".weight"].float()
+            if (name + ".bias") in state_dict:
+                L.bias = state_dict[name + ".bias"].float().to(device)
+            if kind == "conv":
+                if name == "conv_in":
+                    L.w_c4 = W.permute(0, 2, 3, 1).contiguous().to(device=device, dtype=BF16)  # [C][3][3][4]
+                else:
+                    L.w_fwd = W.permute(0, 2, 3, 1).reshape(cout, -1).contiguous().to(device=device, dtype=BF16)
+                    if name == "conv_out":
+                        L.w_c4_t = W.permute(1, 2, 3, 0).contiguous().to(device=device, dtype=BF16)  # [C][3][3][4]
+                    elif need_backward:
+                        L.w_t = W.permute(1, 2, 3, 0).reshape(cin, -1).contiguous().to(device=device, dtype=BF16)
+            else:
+                L.w_fwd = W.contiguous().to(device=device, dtype=BF16)
+                if need_backward and not name.endswith(no_dgrad) and not name.startswith("time_embedding"):
+                    L.w_t = W.t().contiguous().to(device=device, dtype=BF16)
+            if lora and is_lora_target(name):
+                taps = k * k if kind == "conv" else 1
+                A = state_dict[name + ".lora_A.weight"].float()
+                Bm = state_dict[name + ".lora_B.weight"].float()
+                if kind == "conv":
+                    A = A.permute(0, 2, 3, 1)
+                A = A.reshape(self.r, taps * cin)
+                Bm = Bm.reshape(cout, self.r)
+                lo = _Lora()
+                lo.a_off, lo.b_off = moff, moff + A.numel()
+                moff += A.numel() + Bm.numel()
+                master += [A.flatten(), Bm.flatten()]
+                lo.opnd_off = opnd_total
+                opnd_total += 2 * A.numel() + 2 * Bm.numel()
+                L.lora = lo
+                entries.append((L, taps))
+            self.layers[name] = L
+        self.lora_layers = [e[0] for e in entries]
+        if lora and entries:
+            self.lora_master = torch.cat(master).to(device)
+            self.lora_grad = torch.zeros_like(self.lora_master)
+            self.lora_opnd = torch.empty(opnd_total, device=device, dtype=BF16)
+            rows, work = [], 0
+            for L, taps in entries:
+                lo = L.lora
+                na, nb = self.r * taps * L.cin, L.cout * self.r
+                o = lo.opnd_off
+                a_fwd, sb_fwd, sb_t, a_t = o, o + na, o + na + nb, o + na + 2 * nb
+                lo.a_fwd = self.lora_opnd[a_fwd:a_fwd + na].view(self.r, taps * L.cin)
+                lo.sb_fwd = self.lora_opnd[sb_fwd:sb_fwd + nb].view(L.cout, self.r)
+                lo.sb_t = self.lora_opnd[sb_t:sb_t + nb].view(self.r, L.cout)
+                lo.a_t = self.lora_opnd[a_t:a_t + na].view(L.cin, taps * self.r)
+                lo.gA = self.lora_grad[lo.a_off:lo.a_off + na].view(self.r, taps * L.cin)
+                lo.gB = self.lora_grad[lo.b_off:lo.b_off + nb].view(L.cout, self.r)
+                rows.append([lo.a_off, lo.b_off, a_fwd, sb_fwd, sb_t, a_t, L.cin | (taps << 32),
+                             L.cout | (self.r << 32), work])
+                work += na + nb
+            self.refresh_table = torch.tensor(rows, dtype=torch.int64, device=device)
+            self.refresh_work = work
+            self.refresh_lora()
+        self.saved = None
+
+    # ------------------------------------------------------------------------------------
+    def refresh_lora(self):
+        """Regenerate the bf16 GEMM operand copies (A, s*B, (s*B)^T, A^T) from the fp32 masters."""
+        ops._call("pcm_lora_refresh", self.lora_master.data_ptr(), self.refresh_table.data_ptr(),
+                  self.refresh_table.shape[0], self.refresh_work, self.scale, self.lora_opnd.data_ptr())
+
+    def lora_state_dict(self):
+        """peft-style tensors (`<module>.lora_A.weight` [r, cin(,k,k)], `.lora_B.weight`)."""
+        out = {}
+        for L in self.lora_layers:
+            lo = L.lora
+            taps = L.k * L.k if L.kind == "conv" else 1
+            A = self.lora_master[lo.a_off:lo.a_off + self.r * taps * L.cin]
+            Bm = self.lora_master[lo.b_off:lo.b_off + L.cout * self.r]
+            if L.kind == "conv":
+                out[L.name + ".lora_A.weight"] = A.view(self.r, L.k, L.k, L.cin).permute(0, 3, 1, 2).contiguous()
+                out[L.name + ".lora_B.weight"] = Bm.view(L.cout, self.r, 1, 1).clone()
+            else:
+                out[L.name + ".lora_A.weight"] = A.view(self.r, L.cin).clone()
+                out[L.name + ".lora_B.weight"] = Bm.view(L.cout, self.r).clone()
+        return out
+
+    def lora_grad_dict(self):
+        out = {}
+        for L in self.lora_layers:
+            lo = L.lora
+            if L.kind == "conv":
+                out[L.name + ".lora_A.weight"] = lo.gA.view(self.r, L.k, L.k, L.cin).permute(0, 3, 1, 2).contiguous()
+                out[L.name + ".lora_B.weight"] = lo.gB.view(L.cout, self.r, 1, 1).clone()
+            else:
+                out[L.name + ".lora_A.weight"] = lo.gA.clone()
+                out[L.name + ".lora_B.weight"] = lo.gB.clone()
+        return out
+
+    # ------------------------------------------------------------------------------------
+    # primitive layers (forward)
+    # ------------------------------------------------------------------------------------
+    def _new(self, *shape, dtype=BF16):
+        return torch.empty(*shape, device=self.dev, dtype=dtype)
+
+    def _conv_prog(self, xs, k, stride, cin_total):
+        """(a_srcs, prog) of a k x k convolution over channel-concatenated sources xs."""
+        if stride == 2:
+            x = xs[0]
+            planes = [x[:, p::2, q::2, :] for p in range(2) for q in range(2)]
+            srcs = [ops.asrc_nhwc(pl) for pl in planes]
+            prog = []
+            for kh in range(3):
+                for kw in range(3):
+                    p, dh = _S2[kh]
+                    q, dw = _S2[kw]
+                    prog.append((p * 2 + q, 0, dw, dh, cin_total // 64, 0, (kh * 3 + kw) * cin_total))
+            return srcs, prog
+        srcs = [ops.asrc_nhwc(x) for x in xs]
+        taps = TAPS3 if k == 3 else [(0, 0)]
+        prog, coff = [], 0
+        for si, x in enumerate(xs):
+            ci = x.shape[-1]
+            for t, (dw, dh) in enumerate(taps):
+                prog.append((si, 0, dw, dh, ci // 64, 0, t * cin_total + coff))
+            coff += ci
+        return srcs, prog
+
+    def conv3(self, name, xs, lora, stride=1, rowvec=None, residual=None, out_fp32=False, save=None):
+        """3x3 pad-1 convolution (+LoRA) over NHWC sources xs (channel concat), fused epilogue."""
+        L = self.layers[name]
+        B, H, W, _ = xs[0].shape
+        Ho, Wo = H // stride, W // stride
+        M, N = B * Ho * Wo, L.cout
+        srcs, prog = self._conv_prog(xs, 3, stride, L.cin)
+        bs = [ops.bsrc(L.w_fwd)]
+        T = None
+        if lora and L.lora is not None:
+            T = self._new(B, Ho, Wo, self.r)
+            ops.gemm(srcs, [ops.bsrc(L.lora.a_fwd)], prog, lin=False, M=M, N=self.r, geo=(Wo, Ho),
+                     out=T.view(M, self.r))
+            prog = prog + [(len(srcs), 1, 0, 0, 1, 0, 0)]
+            srcs = srcs + [ops.asrc_nhwc(T)]
+            bs.append(ops.bsrc(L.lora.sb_fwd))
+        out = self._new(B, Ho, Wo, N, dtype=torch.float32 if out_fp32 else BF16)
+        ops.gemm(srcs, bs, prog, lin=False, M=M, N=N, geo=(Wo, Ho), out=out.view(M, N), bias=L.bias,
+                 rowvec=rowvec, residual=None if residual is None else residual.reshape(M, N),
+                 round_bf16=out_fp32)
+        if save is not None:
+            save.append(("conv3", name, xs, T, stride))
+        return out
+
+    def linear(self, name, xs, lora, residual=None, act=0, save=None):
+        """nn.Linear / 1x1 conv over [M, C] matrices xs (channel concat) (+LoRA), fused epilogue."""
+        L = self.layers[name]
+        M, N = xs[0].shape[0], L.cout
+        srcs = [ops.asrc_mat(x) for x in xs]
+        prog, coff = [], 0
+        for si, x in enumerate(xs):
+            prog.append((si, 0, 0, 0, x.shape[1] // 64, 0, coff))
+            coff += x.shape[1]
+        bs = [ops.bsrc(L.w_fwd)]
+        T = None
+        if lora and L.lora is not None:
+            T = self._new(M, self.r)
+            ops.gemm(srcs, [ops.bsrc(L.lora.a_fwd)], prog, lin=True, M=M, N=self.r, out=T)
+            prog = prog + [(len(srcs), 1, 0, 0, 1, 0, 0)]
+            srcs = srcs + [ops.asrc_mat(T)]
+            bs.append(ops.bsrc(L.lora.sb_fwd))
+        out = self._new(M, N)
+        ops.gemm(srcs, bs, prog, lin=True, M=M, N=N, out=out, bias=L.bias, residual=residual, act=act)
+        if save is not None:
+            save.append(("linear", name, xs, T))
+        return out
+
+    def gn(self, name, xs, B, HW, eps, silu, save=None):
+        L = self.layers[name]
+        C = sum(x.shape[-1] for x in xs)
+        out = self._new(B * HW, C)
+        stats = self._new(B, self.cfg.norm_num_groups, 2, dtype=torch.float32)
+        ops.groupnorm_fwd(xs[0], xs[1] if len(xs) > 1 else None, L.gamma, L.beta, eps, silu, out, stats,
+                          B, HW, self.cfg.norm_num_groups)
+        if save is not None:
+            save.append(("gn", name, xs, stats, eps, silu, B, HW))
+        return out
+
+    def ln(self, name, x, save=None):
+        L = self.layers[name]
+        out = torch.empty_like(x)
+        stats = self._new(x.shape[0], 2, dtype=torch.float32)
+        ops.layernorm_fwd(x, L.gamma, L.beta, out, stats)
+        if save is not None:
+            save.append(("ln", name, x, stats))
+        return out
+
+    def attention(self, q, k, v, B, Sq, Skv, save=None):
+        Hh = self.cfg.num_heads
+        D = q.shape[1] // Hh
+        out = torch.empty_like(q)
+        lse = self._new(B, Hh, Sq, dtype=torch.float32)
+        ops.attn_fwd(q, k, v, out, lse, B, Hh, Sq, Skv, D, D ** -0.5)
+        if save is not None:
+            save.append(("attn", q, k, v, out, lse, B, Sq, Skv))
+        return out
+
+    # ------------------------------------------------------------------------------------
+    # blocks (forward)
+    # ------------------------------------------------------------------------------------
+    def resnet(self, p, xs, st, lora, save):
+        """xs: list of NHWC sources (skip concat = 2 sources).  Returns [B,H,W,Cout]."""
+        B, H, W, _ = xs[0].shape
+        HW = H * W
+        cin = sum(x.shape[-1] for x in xs)
+        cout = self.layers[p + ".conv1"].cout
+        flat = [x.view(B * HW, x.shape[-1]) for x in xs]
+        h = self.gn(p + ".norm1", flat, B, HW, 1e-5, True, save)
+        tproj = self.linear(p + ".time_emb_proj", [st], lora, save=save)
+        h = self.conv3(p + ".conv1", [h.view(B, H, W, cin)], lora, rowvec=tproj, save=save)
+        h = self.gn(p + ".norm2", [h.view(B * HW, cout)], B, HW, 1e-5, True, save)
+        if cin != cout:
+            sc = self.linear(p + ".conv_shortcut", flat, lora, save=save).view(B, H, W, cout)
+        else:
+            sc = xs[0]
+        return self.conv3(p + ".conv2", [h.view(B, H, W, cout)], lora, residual=sc, save=save)
+
+    def transformer(self, p, x, ctx, lora, save):
+        B, H, W, C = x.shape
+        S, M = H * W, B * H * W
+        xf = x.view(M, C)
+        t = p + ".transformer_blocks.0"
+        g = self.gn(p + ".norm", [xf], B, S, 1e-6, False, save)
+        h = self.linear(p + ".proj_in", [g], lora, save=save)
+        n = self.ln(t + ".norm1", h, save)
+        q = self.linear(t + ".attn1.to_q", [n], lora, save=save)
+        k = self.linear(t + ".attn1.to_k", [n], lora, save=save)
+        v = self.linear(t + ".attn1.to_v", [n], lora, save=save)
+        a = self.attention(q, k, v, B, S, S, save)
+        h = self.linear(t + ".attn1.to_out.0", [a], lora, residual=h, save=save)
+        n = self.ln(t + ".norm2", h, save)
+        q = self.linear(t + ".attn2.to_q", [n], lora, save=save)
+        k = self.linear(t + ".attn2.to_k", [ctx], lora, save=save)
+        v = self.linear(t + ".attn2.to_v", [ctx], lora, save=save)
+        a = self.attention(q, k, v, B, S, ctx.shape[0] // B, save)
+        h = self.linear(t + ".attn2.to_out.0", [a], lora, residual=h, save=save)
+        n = self.ln(t + ".norm3", h, save)
+        u = self.linear(t + ".ff.net.0.proj", [n], lora, save=save)
+        gg = self._new(M, u.shape[1] // 2)
+        ops.geglu_fwd(u, gg)
+        if save is not None:
+            save.append(("geglu", u))
+        h = self.linear(t + ".ff.net.2", [gg], lora, residual=h, save=save)
+        return self.linear(p + ".proj_out", [h], lora, residual=xf, save=save).view(B, H, W, C)
+
+    def forward(self, sample, timesteps, ctx, lora=True, save=False):
+        """sample: fp32 [B,H,W,4] NHWC; timesteps: int64 [B]; ctx: bf16 [B*77, D].
+        Returns eps fp32 [B,H,W,4] (values rounded to bf16 like the autocast output)."""
+        cfg = self.cfg
+        lora = lora and self.has_lora
+        tape = [] if save else None
+        B, H, W, _ = sample.shape
+        c0 = cfg.block_out_channels[0]
+        emb = self._new(B, c0)
+        ops.timestep_embed(timesteps, emb)
+        hemb = self.linear("time_embedding.linear_1", [emb], False, act=1)
+        st = self.linear("time_embedding.linear_2", [hemb], False, act=1)  # silu(temb)
+        x = self._new(B, H, W, c0)
+        Lci = self.layers["conv_in"]
+        ops.conv3x3_c4(sample, Lci.w_c4, Lci.bias, x, sgn=1, round_in=True)
+        skips = [x]
+        nb = len(cfg.block_out_channels)
+        marks = []  # tape segment boundaries for the backward walk
+        for i in range(nb):
+            for j in range(cfg.layers_per_block):
+                x = self._block(tape, marks, "res", f"down_blocks.{i}.resnets.{j}", [x], st, lora)
+                if cfg.down_attn[i]:
+                    x = self._block(tape, marks, "attn", f"down_blocks.{i}.attentions.{j}", x, ctx, lora)
+                skips.append(x)
+            if i < nb - 1:
+                x = self._block(tape, marks, "down", f"down_blocks.{i}.downsamplers.0.conv", x, None, lora)
+                skips.append(x)
+        x = self._block(tape, marks, "res", "mid_block.resnets.0", [x], st, lora)
+        x = self._block(tape, marks, "attn", "mid_block.attentions.0", x, ctx, lora)
+        x = self._block(tape, marks, "res", "mid_block.resnets.1", [x], st, lora)
+        for i in range(nb):
+            for j in range(cfg.layers_per_block + 1):
+                x = self._block(tape, marks, "res", f"up_blocks.{i}.resnets.{j}", [x, skips.pop()], st, lora)
+                if cfg.up_attn[i]:
+                    x = self._block(tape, marks, "attn", f"up_blocks.{i}.attentions.{j}", x, ctx, lora)
+            if i < nb - 1:
+                x = self._block(tape, marks, "up", f"up_blocks.{i}.upsamplers.0.conv", x, None, lora)
+        Bx, Hx, Wx, Cx = x.shape
+        g = self.gn("conv_norm_out", [x.view(Bx * Hx * Wx, Cx)], Bx, Hx * Wx, 1e-5, True, tape)
+        eps = self.conv3("conv_out", [g.view(Bx, Hx, Wx, Cx)], False, out_fp32=True)
+        if save:
+            self.saved = (tape, marks, (B, H, W))
+        return eps
+
+    def _block(self, tape, marks, kind, name, x, aux, lora):
+        start = len(tape) if tape is not None else 0
+        if kind == "res":
+            out = self.resnet(name, x, aux, lora, tape)
+        elif kind == "attn":
+            out = self.transformer(name, x, aux, lora, tape)
+        elif kind == "down":
+            out = self.conv3(name, [x], lora, stride=2, save=tape)
+        else:  # up: nearest 2x then conv
+            B, H, W, C = x.shape
+            xu = self._new(B, 2 * H, 2 * W, C)
+            ops.upsample2x_fwd(x, xu)
+            out = self.conv3(name, [xu], lora, save=tape)
+        if tape is not None:
+            marks.append((kind, name, start, len(tape)))
+        return out
+
+    # ------------------------------------------------------------------------------------
+    # backward primitives
+    # ------------------------------------------------------------------------------------
+    def _lora_wgrads(self, L, P_list, dy_mat, T_mat, dt_mat, taps_desc, lin, geo, M):
+        """dB += s * dy^T T ;  dA += dt^T x  (per source / tap group)."""
+        lo = L.lora
+        ops.wgrad(ops.asrc_mat(dy_mat), ops.asrc_mat(T_mat), lo.gB, lin=True, M=M, os_row=self.r, os_col=1)
+        ktot = lo.gA.shape[1]
+        for (psrc, taps, offs) in P_list:
+            ops.wgrad(psrc, taps_desc(dt_mat), lo.gA, lin=lin, M=M, geo=geo, taps=taps, tap_off=offs,
+                      os_row=1, os_col=ktot)
+
+    def linear_bwd(self, rec, dy, need_dx=True, accumulate=None):
+        """rec = ("linear", name, xs, T).  Returns dx [M, cin_total] (or None)."""
+        _, name, xs, T = rec
+        L = self.layers[name]
+        M = dy.shape[0]
+        srcs, bs = [ops.asrc_mat(dy)], None
+        dt = None
+        if T is not None:
+            dt = self._new(M, self.r)
+            ops.gemm([ops.asrc_mat(dy)], [ops.bsrc(L.lora.sb_t)], [(0, 0, 0, 0, L.cout // 64, 0, 0)],
+                     lin=True, M=M, N=self.r, out=dt)
+            P_list, coff = [], 0
+            for x in xs:
+                P_list.append((ops.asrc_mat(x), ((0, 0),), (coff,)))
+                coff += x.shape[1]
+            self._lora_wgrads(L, P_list, dy, T, dt, ops.asrc_mat, True, (1, 1), M)
+        if not need_dx:
+            return None
+        prog = [(0, 0, 0, 0, L.cout // 64, 0, 0)]
+        bs = [ops.bsrc(L.w_t)]
+        if dt is not None:
+            srcs.append(ops.asrc_mat(dt))
+            bs.append(ops.bsrc(L.lora.a_t))
+            prog.append((1, 1, 0, 0, 1, 0, 0))
+        dx = self._new(M, L.cin)
+        ops.gemm(srcs, bs, prog, lin=True, M=M, N=L.cin, out=dx, residual=accumulate)
+        return dx
+
+    def conv3_bwd(self, rec, dy, need_dx=True, accumulate=None):
+        """rec = ("conv3", name, xs, T, stride); dy [B,Ho,Wo,N].  Returns dx [B,H,W,cin_total]."""
+        _, name, xs, T, stride = rec
+        L = self.layers[name]
+        B, Ho, Wo, N = dy.shape
+        M = B * Ho * Wo
+        geo = (Wo, Ho)
+        dy_m = dy.view(M, N)
+        dt = None
+        if T is not None:
+            dt = self._new(B, Ho, Wo, self.r)
+            ops.gemm([ops.asrc_mat(dy_m)], [ops.bsrc(L.lora.sb_t)], [(0, 0, 0, 0, N // 64, 0, 0)],
+                     lin=True, M=M, N=self.r, out=dt.view(M, self.r))
+            P_list = []
+            if stride == 1:
+                coff = 0
+                for x in xs:
+                    P_list.append((ops.asrc_nhwc(x), TAPS3, [t * L.cin + coff for t in range(9)]))
+                    coff += x.shape[-1]
+            else:
+                x = xs[0]
+                for p in range(2):
+                    for q in range(2):
+                        taps, offs = [], []
+                        for kh in range(3):
+                            for kw in range(3):
+                                if _S2[kh][0] == p and _S2[kw][0] == q:
+                                    taps.append((_S2[kw][1], _S2[kh][1]))
+                                    offs.append((kh * 3 + kw) * L.cin)
+                        P_list.append((ops.asrc_nhwc(x[:, p::2, q::2, :]), taps, offs))
+            lo = L.lora
+            ops.wgrad(ops.asrc_mat(dy_m), ops.asrc_mat(T.view(M, self.r)), lo.gB, lin=True, M=M,
+                      os_row=self.r, os_col=1)
+            ktot = lo.gA.shape[1]
+            for (psrc, taps, offs) in P_list:
+                ops.wgrad(psrc, ops.asrc_nhwc(dt), lo.gA, lin=False, M=M, geo=geo, taps=taps, tap_off=offs,
+                          os_row=1, os_col=ktot)
+        if not need_dx:
+            return None
+        cin = L.cin
+        if stride == 1:
+            srcs, bs = [ops.asrc_nhwc(dy)], [ops.bsrc(L.w_t)]
+            prog = [(0, 0, -dw, -dh, N // 64, 0, t * N) for t, (dw, dh) in enumerate(TAPS3)]
+            if dt is not None:
+                srcs.append(ops.asrc_nhwc(dt))
+                bs.append(ops.bsrc(L.lora.a_t))
+                prog += [(1, 1, -dw, -dh, 1, 0, t * self.r) for t, (dw, dh) in enumerate(TAPS3)]
+            dx = self._new(B, Ho, Wo, cin)
+            ops.gemm(srcs, bs, prog, lin=False, M=M, N=cin, geo=geo, out=dx.view(M, cin),
+                     residual=None if accumulate is None else accumulate.reshape(M, cin))
+            return dx
+        # stride 2: one launch per parity plane of dx
+        H, W = 2 * Ho, 2 * Wo
+        dx = self._new(B, H, W, cin)
+        for p in range(2):
+            for q in range(2):
+                # x row 2i'+p receives dy row i'+s through kernel row kh: p=0 -> (kh=1, s=0);
+                # p=1 -> (kh=0, s=+1), (kh=2, s=0)
+                khs = [(1, 0)] if p == 0 else [(0, 1), (2, 0)]
+                kws = [(1, 0)] if q == 0 else [(0, 1), (2, 0)]
+                srcs, bs, prog, lprog = [ops.asrc_nhwc(dy)], [ops.bsrc(L.w_t)], [], []
+                for kh, sh in khs:
+                    for kw, sw in kws:
+                        t = kh * 3 + kw
+                        prog.append((0, 0, sw, sh, N // 64, 0, t * N))
+                        lprog.append((1, 1, sw, sh, 1, 0, t * self.r))
+                if dt is not None:
+                    srcs.append(ops.asrc_nhwc(dt))
+                    bs.append(ops.bsrc(L.lora.a_t))
+                    prog += lprog
+                plane = dx[:, p::2, q::2, :]
+                acc = None if accumulate is None else accumulate[:, p::2, q::2, :]
+                ops.gemm(srcs, bs, prog, lin=False, M=M, N=cin, geo=geo, out=plane, residual=acc,
+                         out_strides=(plane.stride(2), plane.stride(1), plane.stride(0)), epi=(Wo, Wo * Ho))
+        return dx
+
+    def gn_bwd(self, rec, dy, add=None):
+        _, name, xs, stats, eps, silu, B, HW = rec
+        L = self.layers[name]
+        dx1 = torch.empty_like(xs[0])
+        dx2 = torch.empty_like(xs[1]) if len(xs) > 1 else None
+        red = self._new(B, self.cfg.norm_num_groups, 2, dtype=torch.float32)
+        ops.groupnorm_bwd(dy, xs[0], xs[1] if len(xs) > 1 else None, L.gamma, L.beta, eps, silu, stats, red,
+                          add, dx1, dx2, B, HW, self.cfg.norm_num_groups)
+        return dx1, dx2
+
+    def ln_bwd(self, rec, dy, add=None):
+        _, name, x, stats = rec
+        dx = torch.empty_like(x)
+        ops.layernorm_bwd(dy, x, self.layers[name].gamma, stats, add, dx)
+        return dx
+
+    def attn_bwd(self, rec, dout):
+        _, q, k, v, out, lse, B, Sq, Skv = rec
+        Hh = self.cfg.num_heads
+        D = q.shape[1] // Hh
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        delta = torch.empty_like(lse)
+        ops.attn_bwd(q, k, v, out, dout, lse, delta, dq, dk, dv, B, Hh, Sq, Skv, D, D ** -0.5)
+        return dq, dk, dv
+
+    # ------------------------------------------------------------------------------------
+    # block backward (records were appended in forward order)
+    # ------------------------------------------------------------------------------------
+    def resnet_bwd(self, recs, dout, need_dx=True):
+        """recs: [gn1, temb linear, conv1, gn2, (shortcut linear), conv2].  dout [B,H,W,Cout].
+        Returns (dx1, dx2) for the (possibly concatenated) input sources."""
+        has_sc = len(recs) == 6
+        gn1, tlin, conv1, gn2 = recs[0], recs[1], recs[2], recs[3]
+        conv2 = recs[-1]
+        B, H, W, cout = dout.shape
+        M = B * H * W
+        dh2 = self.conv3_bwd(conv2, dout)                              # grad wrt silu(gn2(h1))
+        dh1, _ = self.gn_bwd(gn2, dh2.view(M, cout))                   # grad wrt h1 [M, cout]
+        # time embedding branch: d tproj[b, n] = sum_hw dh1
+        drow = self._new(B, cout)
+        ops.colsum(dh1, drow, B, H * W)
+        self.linear_bwd(tlin, drow, need_dx=False)
+        dh = self.conv3_bwd(conv1, dh1.view(B, H, W, cout), need_dx=need_dx)
+        dsc = self.linear_bwd(recs[4], dout.view(M, cout), need_dx=need_dx) if has_sc else dout.view(M, cout)
+        if not need_dx:
+            return None, None
+        return self.gn_bwd(gn1, dh.view(M, -1), add=dsc)
+
+    def transformer_bwd(self, recs, dout):
+        """recs order as appended by transformer(); dout [B,H,W,C]; returns dx [B,H,W,C]."""
+        (gn, pin, ln1, lq, lk, lv, at1, lo1, ln2, lq2, lk2, lv2, at2, lo2, ln3, ff1, gegl, ff2, pout) = recs
+        B, H, W, C = dout.shape
+        M = B * H * W
+        do = dout.view(M, C)
+        dh3 = self.linear_bwd(pout, do)
+        dgg = self.linear_bwd(ff2, dh3)
+        u = gegl[1]
+        du = torch.empty_like(u)
+        ops.geglu_bwd(dgg, u, du)
+        dn3 = self.linear_bwd(ff1, du)
+        dh2 = self.ln_bwd(ln3, dn3, add=dh3)
+        da2 = self.linear_bwd(lo2, dh2)
+        dq2, dk2, dv2 = self.attn_bwd(at2, da2)
+        self.linear_bwd(lk2, dk2, need_dx=False)
+        self.linear_bwd(lv2, dv2, need_dx=False)
+        dn2 = self.linear_bwd(lq2, dq2)
+        dh1 = self.ln_bwd(ln2, dn2, add=dh2)
+        da1 = self.linear_bwd(lo1, dh1)
+        dq, dk, dv = self.attn_bwd(at1, da1)
+        dn1 = self.linear_bwd(lq, dq)
+        dn1 = self.linear_bwd(lk, dk, accumulate=dn1)
+        dn1 = self.linear_bwd(lv, dv, accumulate=dn1)
+        dh0 = self.ln_bwd(ln1, dn1, add=dh1)
+        dg = self.linear_bwd(pin, dh0)
+        dx, _ = self.gn_bwd(gn, dg, add=do)
+        return dx.view(B, H, W, C)
+
+    def backward(self, d_eps):
+        """d_eps: fp32 [B,H,W,4] gradient of the loss w.r.t. the student epsilon.
+        Accumulates LoRA gradients into self.lora_grad (caller zeroes it between steps)."""
+        tape, marks, (B, H, W) = self.saved
+        cfg = self.cfg
+        c0 = cfg.block_out_channels[0]
+        Lco = self.layers["conv_out"]
+        dg = self._new(B, H, W, c0)
+        ops.conv3x3_c4(d_eps, Lco.w_c4_t, None, dg, sgn=-1, round_in=False)
+        d, _ = self.gn_bwd(tape[-1], dg.view(B * H * W, c0))
+        d = d.view(B, H, W, c0)
+        nb = len(cfg.block_out_channels)
+        mi = len(marks) - 1
+        dskips = []
+
+        def pop():
+            nonlocal mi
+            kind, name, s, e = marks[mi]
+            mi -= 1
+            return kind, tape[s:e]
+
+        # up path (reverse)
+        for i in reversed(range(nb)):
+            if i < nb - 1:
+                _, recs = pop()
+                dxu = self.conv3_bwd(recs[0], d)
+                Bu, Hu, Wu, Cu = dxu.shape
+                d = self._new(Bu, Hu // 2, Wu // 2, Cu)
+                ops.upsample2x_bwd(dxu, d)
+            for j in reversed(range(cfg.layers_per_block + 1)):
+                if cfg.up_attn[i]:
+                    _, recs = pop()
+                    d = self.transformer_bwd(recs, d)
+                _, recs = pop()
+                d1, d2 = self.resnet_bwd(recs, d)
+                Bc, Hc, Wc, _ = d.shape
+                dskips.append(d2.view(Bc, Hc, Wc, -1))
+                d = d1.view(Bc, Hc, Wc, -1)
+        # mid
+        for kind in ("res", "attn", "res"):
+            k_, recs = pop()
+            if k_ == "attn":
+                d = self.transformer_bwd(recs, d)
+            else:
+                Bc, Hc, Wc, _ = d.shape
+                d = self.resnet_bwd(recs, d)[0].view(Bc, Hc, Wc, -1)
+        # down path (reverse); dskips is ordered s0..s11 reversed consumption -> s_last first
+        def add_skip(dcur):
+            ds = dskips_by_idx.pop()
+            out = torch.empty_like(dcur)
+            ops.add_bf16(dcur, ds, out)
+            return out
+
+        # up-path backward visited resnets in reverse, so dskips = [ds_0, ds_1, ..., ds_11]
+        dskips_by_idx = dskips  # pop() from the end = highest skip index first
+        for i in reversed(range(nb)):
+            if i < nb - 1:
+                d = add_skip(d)
+                _, recs = pop()
+                d = self.conv3_bwd(recs[0], d)
+            for j in reversed(range(cfg.layers_per_block)):
+                d = add_skip(d)
+                if cfg.down_attn[i]:
+                    _, recs = pop()
+                    d = self.transformer_bwd(recs, d)
+                _, recs = pop()
+                first = (i == 0 and j == 0)
+                Bc, Hc, Wc, _ = d.shape
+                r = self.resnet_bwd(recs, d, need_dx=not first)
+                if not first:
+                    d = r[0].view(Bc, Hc, Wc, -1)
+        self.saved = None

@@ -1,0 +1,119 @@
+"""Whole-network and whole-step parity of the B200 path against the CPU oracle (oracle/unet_ref.py,
+oracle/pcm_ref.py) on identical seeded weights and inputs.
+
+Tolerances: the CUDA path computes in bf16 with fp32 accumulation; the oracle is run in its
+bf16-emulating mode (rounds the same tensors), so differences are accumulation-order noise.
+  * eps tensors: max error <= 3e-2 * max|ref|, mean error <= 1e-2 * rms(ref)
+  * per-step loss: relative error <= 1e-3 (the north-star tolerance)
+  * LoRA gradients: global relative L2 error <= 5e-2, cosine >= 0.995
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+BF = torch.bfloat16
+
+
+def _nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def _nchw(x):
+    return x.permute(0, 3, 1, 2).contiguous()
+
+
+def _relerr(a, b):
+    return ((a.float() - b.float()).norm() / (b.float().norm() + 1e-12)).item()
+
+
+def _setup(cfg_name, B, hw, seed=0):
+    from oracle import unet_ref, pcm_ref
+    from pcm_b200 import config
+    ocfg = getattr(unet_ref, cfg_name)
+    pcfg = getattr(config, cfg_name)
+    P = unet_ref.init_params(ocfg, seed)
+    batch = pcm_ref.make_batch(ocfg, B, hw, seed=seed)
+    return ocfg, pcfg, P, batch
+
+
+@pytest.mark.parametrize("cfg_name,B,hw", [("TINY", 2, 16), ("TINY", 3, 8)])
+def test_unet_forward_matches_oracle(cuda, cfg_name, B, hw):
+    from oracle import unet_ref
+    from pcm_b200.unet import UNetB200
+    ocfg, pcfg, P, batch = _setup(cfg_name, B, hw)
+    net = UNetB200(pcfg, P, cuda)
+    x = batch["latents"]
+    ts = torch.tensor([999, 19, 499][:B])
+    ctx = batch["prompt_embeds"]
+    for lora in (True, False):
+        ref = unet_ref.UNetRef(ocfg, P, use_lora=lora, emulate_bf16=True)(x, ts, ctx)
+        out = net.forward(_nhwc(x).to(cuda), ts.to(cuda), ctx.to(cuda).to(BF).reshape(B * 77, -1), lora=lora)
+        out = _nchw(out).cpu()
+        err = (out - ref).abs()
+        assert err.max().item() <= 3e-2 * ref.abs().max().item(), (lora, err.max().item(), ref.abs().max().item())
+        assert err.mean().item() <= 1e-2 * ref.pow(2).mean().sqrt().item(), (lora, err.mean().item())
+    # LoRA must matter (B != 0) or the test is vacuous
+    a = net.forward(_nhwc(x).to(cuda), ts.to(cuda), ctx.to(cuda).to(BF).reshape(B * 77, -1), lora=True)
+    b = net.forward(_nhwc(x).to(cuda), ts.to(cuda), ctx.to(cuda).to(BF).reshape(B * 77, -1), lora=False)
+    assert (a - b).abs().max().item() > 1e-3
+
+
+def _run_step(cuda, cfg_name, B, hw, multiphase, seed=0, lr=1e-3):
+    from oracle import pcm_ref
+    from pcm_b200.step import PCMTrainStep
+    ocfg, pcfg, P, batch = _setup(cfg_name, B, hw, seed)
+    ref = pcm_ref.pcm_step_ref(ocfg, P, batch, multiphase=multiphase, emulate_bf16=True)
+    st = PCMTrainStep(pcfg, P, cuda, batch=B, height=hw, width=hw, multiphase=multiphase, lr=lr,
+                      weight_decay=1e-2, keep_debug=True)
+    st.load_inputs(_nhwc(batch["latents"]), _nhwc(batch["noise"]), batch["index"], batch["w"],
+                   batch["prompt_embeds"].to(BF), batch["uncond_prompt_embeds"].to(BF))
+    st.forward_backward()
+    torch.cuda.synchronize()
+    return ocfg, P, batch, ref, st
+
+
+@pytest.mark.parametrize("cfg_name,B,hw,multiphase", [("TINY", 2, 16, 4), ("TINY", 4, 8, 2)])
+def test_step_loss_and_grads_match_oracle(cuda, cfg_name, B, hw, multiphase):
+    from oracle import pcm_ref
+    ocfg, P, batch, ref, st = _run_step(cuda, cfg_name, B, hw, multiphase)
+    assert torch.equal(st.start_t.cpu(), ref["start_timesteps"])
+    assert torch.equal(st.t.cpu(), ref["timesteps"])
+    assert torch.equal(st.end_t.cpu(), ref["end_timesteps"])
+    assert _relerr(_nchw(st.noisy).cpu(), ref["noisy"]) < 5e-3
+    assert _relerr(_nchw(st.x_prev).cpu(), ref["x_prev"]) < 2e-2
+    assert _relerr(_nchw(st.model_pred).cpu(), ref["model_pred"]) < 2e-2
+    assert _relerr(_nchw(st.target).cpu(), ref["target"]) < 2e-2
+    loss, rloss = st.loss.item(), ref["loss"].item()
+    assert abs(loss - rloss) <= 1e-3 * abs(rloss), (loss, rloss)
+    # gradients
+    g = st.unet.lora_grad_dict()
+    num = den = dot = n1 = 0.0
+    for k, rg in ref["grads"].items():
+        gg = g[k].cpu().float()
+        num += (gg - rg).pow(2).sum().item()
+        den += rg.pow(2).sum().item()
+        dot += (gg * rg).sum().item()
+        n1 += gg.pow(2).sum().item()
+    assert den > 0
+    assert (num / den) ** 0.5 <= 5e-2, (num / den) ** 0.5
+    assert dot / (n1 ** 0.5 * den ** 0.5) >= 0.995
+    # optimiser: clip + AdamW on the flat buffer vs the oracle's restatement of T15:1297-1301
+    params = {k: v.clone() for k, v in P.items() if ".lora_" in k}
+    grads = {k: g[k].cpu().float() for k in params}
+    before = st.unet.lora_state_dict()
+    pcm_ref.clip_and_adamw_ref(params, grads, {}, lr=1e-3, weight_decay=1e-2, max_grad_norm=1.0)
+    st.optimizer_step()
+    torch.cuda.synchronize()
+    after = st.unet.lora_state_dict()
+    for k in list(params)[:40]:
+        assert torch.allclose(after[k].cpu(), params[k], rtol=1e-4, atol=1e-6), k
+        assert not torch.equal(after[k].cpu(), before[k].cpu()) or grads[k].abs().max() == 0
+    assert st.unet.lora_grad.abs().max().item() == 0.0  # zero_grad folded into the update
+
+
+def test_step_sd15_config1_loss(cuda):
+    """BASELINE config 1 shape: SD1.5 UNet, 2-phase, bs 1, 256x256 (32x32 latents)."""
+    ocfg, P, batch, ref, st = _run_step(cuda, "SD15", 1, 32, 2)
+    loss, rloss = st.loss.item(), ref["loss"].item()
+    assert abs(loss - rloss) <= 1e-3 * abs(rloss), (loss, rloss)
+    assert _relerr(_nchw(st.debug["eps_student"]).cpu(), ref["eps_student"]) < 3e-2
