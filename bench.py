@@ -1,0 +1,304 @@
+#!/usr/bin/env python
+"""bench.py -- SD1.5 PCM-LoRA distillation steps/sec on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's B200 path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference loop restated on CPU
+
+Workload (BASELINE configs[1]): SD1.5 UNet (859.5 M params, random init), LoRA r=64 on the 278
+target modules, 4-phase PCM, per-GPU batch 8, 512x512 images = 64x64x4 latents, bf16 compute,
+CFG solver on (2 teacher passes), Huber loss, clip 1.0, AdamW.  One "step" = the full iteration
+of train_pcm_lora_sd15.py:1139-1301 on one per-GPU batch.  `value` = per-GPU-batch steps per
+second summed over all ranks (data parallel, weak scaling: global batch = 8 x N).
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "distillation steps/sec (SD1.5 PCM-LoRA, bs=8/GPU)"
+# algorithmic FLOPs (SURVEY.md section 8d / BASELINE.md section 3): per sample 5F + A + 4L
+F_, L_, A_ = 803.6e9, 94.3e9, 126.1e9
+FLOP_PER_SAMPLE_64 = 5 * F_ + A_ + 4 * L_
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", 1370.0), d.get("bf16_tflops", 1602.4), d.get("hbm_gbs", 6589.3), "measured"
+    return 1400.0, 1590.0, 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def synth_batch(cfg, B, hw, seed, pinned=True):
+    """Synthetic inputs of SURVEY.md 8(d), NHWC, on (pinned) host memory."""
+    def g(s):
+        return torch.Generator().manual_seed(seed * 1000 + s)
+    t = dict(
+        latents=torch.randn(B, hw, hw, 4, generator=g(0)),
+        noise=torch.randn(B, hw, hw, 4, generator=g(1)),
+        prompt=torch.randn(B, 77, cfg.cross_attention_dim, generator=g(2)).bfloat16(),
+        uncond=torch.randn(1, 77, cfg.cross_attention_dim, generator=g(3)).repeat(B, 1, 1).bfloat16(),
+        index=torch.randint(0, 50, (B,), generator=g(4)),
+        w=4.0 + torch.rand(B, generator=g(5)),
+    )
+    if pinned and torch.cuda.is_available():
+        t = {k: v.pin_memory() for k, v in t.items()}
+    return t
+
+
+def cpu_reference_sample(threads=None, repeats=1, hw=64, multiphase=4):
+    """Times the restated reference loop (oracle) on the host cores on a bounded sample: ONE sample
+    (1/8 of a per-GPU batch) of the bs-8 512x512 workload, fp32, forward x4 + backward.
+    Returns (seconds per sample-step, cores)."""
+    from oracle import pcm_ref, unet_ref
+    cores = threads or os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = unet_ref.SD15
+    P = unet_ref.init_params(cfg, 0)
+    batch = pcm_ref.make_batch(cfg, 1, hw, seed=0)
+    times = []
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        pcm_ref.pcm_step_ref(cfg, P, batch, multiphase=multiphase, emulate_bf16=False, need_grad=True)
+        times.append(time.perf_counter() - t0)
+    return min(times), cores
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU path (oracle port; diffusers/peft/accelerate are not
+    installable offline so the unmodified reference cannot run).  Rank 0 only."""
+    if rank != 0:
+        return
+    per = []
+    from oracle import pcm_ref, unet_ref
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = unet_ref.SD15
+    P = unet_ref.init_params(cfg, 0)
+    batch = pcm_ref.make_batch(cfg, 1, 64, seed=0)
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        pcm_ref.pcm_step_ref(cfg, P, batch, multiphase=4, emulate_bf16=False, need_grad=True)
+        dt = time.perf_counter() - t0
+        if i >= args.warmup:
+            per.append(dt)
+    t_sample = sum(per) / len(per)
+    value = 1.0 / (8.0 * t_sample)  # a bs-8 step = 8 such samples
+    sample = "1 of the 8 samples of a bs-8 512x512 step (fp32, 4 UNet forwards + backward, torch CPU); value = 1/(8*t)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 8.0 * t_sample * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "SD1.5 PCM-LoRA 4-phase, bs=8/GPU, 512x512 (64x64 latents), CFG solver on",
+                   "note": "reference loop restated on CPU (oracle port); one bounded sample per step"},
+        "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--latent", type=int, default=64)
+    ap.add_argument("--multiphase", type=int, default=4)
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-gemm", action="store_true", default=True)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import torch.distributed as dist
+    from pcm_b200 import config, ops
+    from pcm_b200.step import PCMTrainStep
+    from pcm_b200 import weights
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    pg = None
+    if world > 1:
+        os.environ.setdefault("NCCL_IB_DISABLE", "1")
+        os.environ.setdefault("NCCL_P2P_LEVEL", "NVL")
+        dist.init_process_group("nccl", device_id=dev)
+        pg = dist.group.WORLD
+    cfg = config.SD15
+    B, hw = args.batch, args.latent
+    sd = weights.synthetic_state_dict(cfg, seed=0)   # identical on every rank (DDP broadcast semantics)
+    step = PCMTrainStep(cfg, sd, dev, batch=B, height=hw, width=hw, multiphase=args.multiphase,
+                        lr=5e-6, weight_decay=1e-3, max_grad_norm=1.0, process_group=pg)
+    del sd
+    host = [synth_batch(cfg, B, hw, seed=100 * (rank + 1) + i) for i in range(4)]  # per-rank seeds (T15:797)
+
+    def load(i):
+        h = host[i % len(host)]
+        step.load_inputs(h["latents"], h["noise"], h["index"], h["w"], h["prompt"], h["uncond"])
+
+    load(0)
+    torch.cuda.synchronize()
+    use_graph = not args.no_graph
+    if use_graph:
+        step.capture(warmup=1)
+    launches_per_step = ops.LAUNCHES.get("per_step", None)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-timed run: inputs resident in HBM -------------------------------------
+    for _ in range(args.warmup):
+        step.step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ops.LAUNCHES["count"] = 0
+    e0.record()
+    for _ in range(args.steps):
+        step.step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    ms_per_step = ms / args.steps
+    value = world * 1e3 / ms_per_step
+    loss_last = step.loss.item()
+
+    # ---- end-to-end: pinned-host inputs -> H2D -> step -> loss D2H, every step ------------
+    h2d = sum(v.numel() * v.element_size() for v in host[0].values())
+    for i in range(2):
+        load(i)
+        step.step()
+        step.loss.cpu()
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for i in range(args.steps):
+        load(i)
+        step.step()
+        _ = step.loss.cpu()  # device -> host read of the step's result (the reference's loss.item())
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_e2e], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = t.item()
+    e2e_value = world * 1e3 / (ms_e2e / args.steps)
+
+    # ---- roofline of the dominant kernel (pcm_gemm_kernel): per-launch CUDA events ----------
+    sus, burst, hbm, src = peaks()
+    roof = None
+    if rank == 0:
+        ops.PROFILE = []
+        step.run_eager()   # eager pass, every pcm_gemm launch bracketed by events on its stream
+        torch.cuda.synchronize()
+        recs, ops.PROFILE = ops.PROFILE, None
+        tot_ms = sum(a.elapsed_time(b) for a, b, _ in recs)
+        tot_fl = sum(f for _, _, f in recs)
+        ach = tot_fl / (tot_ms * 1e-3) / 1e12 if tot_ms > 0 else 0.0
+        roof = {"bound": "tensor", "kernel": "pcm_gemm_kernel (tcgen05 implicit GEMM, all conv/linear/LoRA/dgrad launches)",
+                "achieved": ach, "peak": sus, "unit": "TFLOP/s", "frac": ach / sus, "traffic": None,
+                "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({src})",
+                "launches": len(recs), "gemm_ms_per_step": tot_ms, "gemm_flop_per_step": tot_fl,
+                "whole_step_achieved": FLOP_PER_SAMPLE_64 * B * (hw / 64.0) ** 2 / (ms_per_step * 1e-3) / 1e12,
+                "whole_step_frac": FLOP_PER_SAMPLE_64 * B * (hw / 64.0) ** 2 / (ms_per_step * 1e-3) / 1e12 / sus}
+    if world > 1:
+        dist.barrier()
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            t_s, cores = cpu_reference_sample()
+            cpu = {"value": 1.0 / (8.0 * t_s), "unit": "steps/s", "cores": cores, "kind": "port",
+                   "sample": "1 of the 8 samples of one bs-8 512x512 step through the restated reference loop "
+                             f"(oracle, fp32, torch CPU, {cores} threads): {t_s:.2f} s; value = 1/(8*t)"}
+        line = {
+            "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"SD1.5 PCM-LoRA {args.multiphase}-phase, bs={B}/GPU, {hw * 8}x{hw * 8} "
+                                   f"({hw}x{hw}x4 latents), LoRA r=64, CFG solver on, Huber, AdamW",
+                       "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
+                       "cuda_graph": use_graph,
+                       "l2": "working set (1.7 GB weights + >10 GB activations per step) >> 126 MB L2; no flush needed",
+                       "value_definition": "per-GPU-batch steps/s summed over ranks"},
+            "clocks": clocks, "loss": loss_last,
+            "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+            "gpu_launches": int((launches_per_step or 0) * args.steps),
+            "roofline": roof, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -155,6 +155,11 @@ int pcm_noise_travel(const float* x, const float* noise, const float* alphas_cum
                      const int64_t* t_cur, const int64_t* t_tgt, int64_t per, int B, float* out,
                      void* stream);
 
+/* out = ca[b]*x + cb[b]*y in float64: DDIMSolver.ddim_step / ddim_style_multiphase_pred
+ * (T15:313-341) for callers that use the solver object directly */
+int pcm_axpby_f64(const float* x, const float* y, const double* ca, const double* cb, int64_t per,
+                  int B, double* out, void* stream);
+
 /* ---- optimiser on the flat fp32 LoRA buffer (T15:1297-1301) ------------------------------- */
 int pcm_grad_sumsq(const float* g, int64_t n, double* out, void* stream);
 /* state: device float[2] = {lr, step}; step is incremented on device before the update */

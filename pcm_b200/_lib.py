@@ -98,6 +98,7 @@ EXPORTS = [
     "pcm_teacher_step",
     "pcm_loss",
     "pcm_noise_travel",
+    "pcm_axpby_f64",
     "pcm_grad_sumsq",
     "pcm_adamw_clip",
     "pcm_lora_refresh",
@@ -127,6 +128,7 @@ ARGTYPES = {
     "pcm_teacher_step": [P, P, P, P, L64, I, P, P],
     "pcm_loss": [P, P, P, P, P, L64, I, I, F, P, P, P, P, P],
     "pcm_noise_travel": [P, P, P, P, P, L64, I, P, P],
+    "pcm_axpby_f64": [P, P, P, P, L64, I, P, P],
     "pcm_grad_sumsq": [P, L64, P, P],
     "pcm_adamw_clip": [P, P, P, P, L64, P, F, F, F, F, F, F, P, I, P],
     "pcm_lora_refresh": [P, P, I, L64, F, P, P],

@@ -192,6 +192,18 @@ __global__ void pcm_noise_travel_kernel(const float* __restrict__ x, const float
   }
 }
 
+// out[i] = ca[b] * x[i] + cb[b] * y[i] in double (DDIMSolver.ddim_step / multiphase jump, which
+// return float64 tensors in the reference because its alpha table is float64, T15:297-303)
+__global__ void pcm_axpby_f64_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                     const double* __restrict__ ca, const double* __restrict__ cb,
+                                     long long per, long long total, double* __restrict__ out) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long b = i / per;
+    out[i] = ca[b] * static_cast<double>(x[i]) + cb[b] * static_cast<double>(y[i]);
+  }
+}
+
 static inline int grid_for(long long total) {
   long long g = (total + 255) / 256;
   if (g > num_sms() * 8) g = num_sms() * 8;
@@ -250,6 +262,14 @@ extern "C" int pcm_noise_travel(const float* x, const float* noise, const float*
   pcm_noise_travel_kernel<<<grid_for(total), 256, 0, ST(stream)>>>(
       x, noise, acp, reinterpret_cast<const long long*>(t_cur),
       reinterpret_cast<const long long*>(t_tgt), per, total, out);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int pcm_axpby_f64(const float* x, const float* y, const double* ca, const double* cb,
+                             int64_t per, int B, double* out, void* stream) {
+  const long long total = per * B;
+  pcm_axpby_f64_kernel<<<grid_for(total), 256, 0, ST(stream)>>>(x, y, ca, cb, per, total, out);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

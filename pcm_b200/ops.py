@@ -39,6 +39,10 @@ def bsrc(w):
 
 
 _NUM_SMS = None
+# kernel-launch accounting (bench.py `gpu_launches`) and optional per-launch GEMM profiling
+LAUNCHES = {"count": 0}
+PROFILE = None  # list of (start_event, end_event, flops) when enabled
+_KERNELS_PER_CALL = {"pcm_groupnorm_fwd": 2, "pcm_groupnorm_bwd": 2, "pcm_attn_bwd": 3, "pcm_adamw_clip": 2}
 
 
 def num_sms():
@@ -107,6 +111,14 @@ def gemm(a_srcs, b_srcs, prog, *, lin, M, N, out, geo=(1, 1), bias=None, rowvec=
     d.epiW, d.epiHW = epi
     d.alpha = alpha
     d.act = act
+    LAUNCHES["count"] += 1
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        L.check(L.lib().pcm_gemm(C.byref(d), _stream()), "pcm_gemm")
+        e1.record()
+        PROFILE.append((e0, e1, 2.0 * M * N * 64 * sum(e[4] for e in prog)))
+        return out
     L.check(L.lib().pcm_gemm(C.byref(d), _stream()), "pcm_gemm")
     return out
 
@@ -130,6 +142,7 @@ def wgrad(p_src, q_src, out, *, lin, M, geo=(1, 1), taps=((0, 0),), tap_off=(0,)
     d.os_row, d.os_col = os_row, os_col
     d.ksplit = ksplit
     d.alpha = alpha
+    LAUNCHES["count"] += 1
     L.check(L.lib().pcm_wgrad(C.byref(d), _stream()), "pcm_wgrad")
     return out
 
@@ -142,6 +155,7 @@ def _p(t):
 
 
 def _call(name, *args):
+    LAUNCHES["count"] += _KERNELS_PER_CALL.get(name, 1)
     L.check(getattr(L.lib(), name)(*args, torch.cuda.current_stream().cuda_stream), name)
 
 

@@ -129,8 +129,10 @@ class PCMTrainStep:
                 self.run_eager()
         torch.cuda.current_stream().wait_stream(s)
         self.graph = torch.cuda.CUDAGraph()
+        n0 = ops.LAUNCHES["count"]
         with torch.cuda.graph(self.graph):
             self.run_eager()
+        ops.LAUNCHES["per_step"] = ops.LAUNCHES["count"] - n0
         # the warm-up / capture runs must not count as training steps
         self.unet.lora_master.copy_(snap[0])
         self.exp_avg.copy_(snap[1])

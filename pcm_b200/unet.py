@@ -365,7 +365,8 @@ class UNetB200:
     def _lora_wgrads(self, L, P_list, dy_mat, T_mat, dt_mat, taps_desc, lin, geo, M):
         """dB += s * dy^T T ;  dA += dt^T x  (per source / tap group)."""
         lo = L.lora
-        ops.wgrad(ops.asrc_mat(dy_mat), ops.asrc_mat(T_mat), lo.gB, lin=True, M=M, os_row=self.r, os_col=1)
+        ops.wgrad(ops.asrc_mat(dy_mat), ops.asrc_mat(T_mat), lo.gB, lin=True, M=M, os_row=self.r, os_col=1,
+                  alpha=self.scale)
         ktot = lo.gA.shape[1]
         for (psrc, taps, offs) in P_list:
             ops.wgrad(psrc, taps_desc(dt_mat), lo.gA, lin=lin, M=M, geo=geo, taps=taps, tap_off=offs,
@@ -431,7 +432,7 @@ class UNetB200:
                         P_list.append((ops.asrc_nhwc(x[:, p::2, q::2, :]), taps, offs))
             lo = L.lora
             ops.wgrad(ops.asrc_mat(dy_m), ops.asrc_mat(T.view(M, self.r)), lo.gB, lin=True, M=M,
-                      os_row=self.r, os_col=1)
+                      os_row=self.r, os_col=1, alpha=self.scale)
             ktot = lo.gA.shape[1]
             for (psrc, taps, offs) in P_list:
                 ops.wgrad(psrc, ops.asrc_nhwc(dt), lo.gA, lin=False, M=M, geo=geo, taps=taps, tap_off=offs,
