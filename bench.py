@@ -164,7 +164,7 @@ def main():
     ap.add_argument("--multiphase", type=int, default=4)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--profile-gemm", action="store_true", default=True)
+    ap.add_argument("--profile-only", action="store_true", help="one eager step, then exit (for ncu)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -198,6 +198,11 @@ def main():
 
     load(0)
     torch.cuda.synchronize()
+    if args.profile_only:
+        step.run_eager()
+        torch.cuda.synchronize()
+        print("profile-only step done, loss", step.loss.item())
+        return
     use_graph = not args.no_graph
     if use_graph:
         step.capture(warmup=1)
