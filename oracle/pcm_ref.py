@@ -177,7 +177,7 @@ def clip_and_adamw_ref(params, grads, state, *, lr, betas=(0.9, 0.999), eps=1e-8
     """T15:1297-1301: clip_grad_norm_(max_norm) over all LoRA grads, then torch.optim.AdamW.step."""
     keys = sorted(grads)
     total = torch.sqrt(sum((grads[k].double() ** 2).sum() for k in keys)).float()
-    coef = torch.clamp(max_grad_norm / (total + 1e-6), max=1.0)
+    coef = torch.clamp(max_grad_norm / (total + 1e-6), max=1.0) if max_grad_norm > 0 else torch.tensor(1.0)
     state["step"] = state.get("step", 0) + 1
     s = state["step"]
     for k in keys:

@@ -42,13 +42,14 @@ _NUM_SMS = None
 # kernel-launch accounting (bench.py `gpu_launches`) and optional per-launch GEMM profiling
 LAUNCHES = {"count": 0}
 PROFILE = None  # list of (start_event, end_event, flops) when enabled
+DRY_RUN = None  # list: record (kind, info) instead of launching (shape analysis without a GPU)
 _KERNELS_PER_CALL = {"pcm_groupnorm_fwd": 2, "pcm_groupnorm_bwd": 2, "pcm_attn_bwd": 3, "pcm_adamw_clip": 2}
 
 
 def num_sms():
     global _NUM_SMS
     if _NUM_SMS is None:
-        _NUM_SMS = L.lib().pcm_num_sms()
+        _NUM_SMS = 148 if DRY_RUN is not None else L.lib().pcm_num_sms()
     return _NUM_SMS
 
 
@@ -112,6 +113,10 @@ def gemm(a_srcs, b_srcs, prog, *, lin, M, N, out, geo=(1, 1), bias=None, rowvec=
     d.alpha = alpha
     d.act = act
     LAUNCHES["count"] += 1
+    if DRY_RUN is not None:
+        DRY_RUN.append(("gemm", dict(M=M, N=N, K=64 * sum(e[4] for e in prog), bn=d.block_n, lin=int(lin),
+                                     nprog=len(prog), res=residual is not None)))
+        return out
     if PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -143,6 +148,9 @@ def wgrad(p_src, q_src, out, *, lin, M, geo=(1, 1), taps=((0, 0),), tap_off=(0,)
     d.ksplit = ksplit
     d.alpha = alpha
     LAUNCHES["count"] += 1
+    if DRY_RUN is not None:
+        DRY_RUN.append(("wgrad", dict(M=M, Cp=p_src.C, taps=len(taps))))
+        return out
     L.check(L.lib().pcm_wgrad(C.byref(d), _stream()), "pcm_wgrad")
     return out
 
@@ -156,6 +164,9 @@ def _p(t):
 
 def _call(name, *args):
     LAUNCHES["count"] += _KERNELS_PER_CALL.get(name, 1)
+    if DRY_RUN is not None:
+        DRY_RUN.append((name, None))
+        return
     L.check(getattr(L.lib(), name)(*args, torch.cuda.current_stream().cuda_stream), name)
 
 
