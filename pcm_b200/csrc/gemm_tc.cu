@@ -45,6 +45,8 @@ struct alignas(64) GemmParams {
 constexpr int kGemmThreads = 192;
 constexpr int kMaxStages = 8;
 constexpr int kATileBytes = 128 * 128;  // 128 rows x 64 bf16
+constexpr int kStagingBytes = 2 * 128 * 32 * 4;  // epilogue transposition buffers (fp32)
+constexpr int kSmemLimit = 227 * 1024 - 512;     // dynamic smem budget (227 KB max minus static)
 
 __global__ void __launch_bounds__(kGemmThreads, 1)
 pcm_gemm_kernel(const __grid_constant__ GemmParams p) {
@@ -155,39 +157,82 @@ pcm_gemm_kernel(const __grid_constant__ GemmParams p) {
     }
   } else {
     // ===================== epilogue =====================
+    // Two phases per 32-column chunk so that global traffic is coalesced:
+    //   1. each thread owns one accumulator row (TMEM lane): TMEM -> registers -> fp32 staging
+    //      tile in shared memory (16-byte chunks XOR-swizzled by row to stay conflict free);
+    //   2. the 128 epilogue threads re-map to (row, 8-column group): 4 neighbouring lanes cover
+    //      64 contiguous output bytes of one row, read residual / bias / row vector, apply the
+    //      activation and store 16 bytes each.
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
+    const int et = threadIdx.x - 64;  // 0..127
+    const int cg = et & 3;            // 8-column group inside the 32-column chunk
+    const int r0 = et >> 2;           // phase-2 rows: r0 + 32 * i
+    float* stg = reinterpret_cast<float*>(smem + S * stage_bytes);
     int acc = 0;
     uint32_t acc_phase = 0;
+    uint32_t chunk_ctr = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
-      const int m = tm * 128 + row, n0 = tn * p.block_n;
-      const bool valid = m < p.M;
-      long long off = 0;
-      const bf16* rv = nullptr;
-      if (valid) {
-        const int b = m / p.epiHW;
-        const int r = m - b * p.epiHW;
-        const int h = r / p.epiW;
-        const int w = r - h * p.epiW;
-        off = b * p.osB + h * p.osH + w * p.osW;
-        if (p.rowvec) rv = p.rowvec + b * p.rowvec_ld;
+      const int n0 = tn * p.block_n;
+      long long off[4];
+      const bf16* rvp[4];
+      bool valid[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int m = tm * 128 + r0 + 32 * i;
+        valid[i] = m < p.M;
+        off[i] = 0;
+        rvp[i] = nullptr;
+        if (valid[i]) {
+          const int b = m / p.epiHW;
+          const int r = m - b * p.epiHW;
+          const int h = r / p.epiW;
+          const int w = r - h * p.epiW;
+          off[i] = b * p.osB + h * p.osH + w * p.osW;
+          if (p.rowvec) rvp[i] = p.rowvec + b * p.rowvec_ld;
+        }
       }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256;
-      for (int j = 0; j < p.block_n; j += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(taddr + j, v);
-        tmem_ld_wait();
-        if (valid) {
+      const int nchunks = p.block_n >> 5;
+      for (int j = 0; j < nchunks; ++j, ++chunk_ctr) {
+        float* sb = stg + (chunk_ctr & 1) * (128 * 32);
+        {
+          uint32_t v[32];
+          tmem_ld_32x32(taddr + j * 32, v);
+          tmem_ld_wait();
+          if (j == nchunks - 1) {
+            // all TMEM reads of this tile are done: hand the accumulator back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+          }
+          float* srow = sb + row * 32;
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int n = n0 + j + g * 8;
-            if (n >= p.N) break;
-            float f[8];
+          for (int c = 0; c < 8; ++c) {
+            const int cs = c ^ (row & 7);
+            *reinterpret_cast<float4*>(srow + cs * 4) =
+                make_float4(__uint_as_float(v[4 * c]), __uint_as_float(v[4 * c + 1]),
+                            __uint_as_float(v[4 * c + 2]), __uint_as_float(v[4 * c + 3]));
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int n = n0 + j * 32 + cg * 8;
+        if (n < p.N) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[g * 8 + i]) * p.alpha;
+          for (int i = 0; i < 4; ++i) {
+            if (!valid[i]) continue;
+            const int rr = r0 + 32 * i;
+            const float* srow = sb + rr * 32;
+            const float4 a0 = *reinterpret_cast<const float4*>(srow + ((2 * cg) ^ (rr & 7)) * 4);
+            const float4 a1 = *reinterpret_cast<const float4*>(srow + ((2 * cg + 1) ^ (rr & 7)) * 4);
+            float f[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] *= p.alpha;
+            const long long o = off[i];
+            const bf16* rv = rvp[i];
             if (n + 8 <= p.N) {
               if (p.bias) {
                 const float4 b0 = *reinterpret_cast<const float4*>(p.bias + n);
@@ -204,7 +249,7 @@ pcm_gemm_kernel(const __grid_constant__ GemmParams p) {
                 t = unpack_bf16x2(u.w); f[6] += t.x; f[7] += t.y;
               }
               if (p.residual) {
-                const uint4 u = *reinterpret_cast<const uint4*>(p.residual + off + n);
+                const uint4 u = *reinterpret_cast<const uint4*>(p.residual + o + n);
                 float2 t;
                 t = unpack_bf16x2(u.x); f[0] += t.x; f[1] += t.y;
                 t = unpack_bf16x2(u.y); f[2] += t.x; f[3] += t.y;
@@ -213,46 +258,43 @@ pcm_gemm_kernel(const __grid_constant__ GemmParams p) {
               }
               if (p.act == 1) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) f[i] = silu_f(f[i]);
+                for (int e = 0; e < 8; ++e) f[e] = silu_f(f[e]);
               }
               if (p.out_fp32) {
                 if (p.round_bf16) {
 #pragma unroll
-                  for (int i = 0; i < 8; ++i) f[i] = __bfloat162float(__float2bfloat16_rn(f[i]));
+                  for (int e = 0; e < 8; ++e) f[e] = __bfloat162float(__float2bfloat16_rn(f[e]));
                 }
-                float* o = reinterpret_cast<float*>(p.out) + off + n;
-                *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
-                *reinterpret_cast<float4*>(o + 4) = make_float4(f[4], f[5], f[6], f[7]);
+                float* op = reinterpret_cast<float*>(p.out) + o + n;
+                *reinterpret_cast<float4*>(op) = make_float4(f[0], f[1], f[2], f[3]);
+                *reinterpret_cast<float4*>(op + 4) = make_float4(f[4], f[5], f[6], f[7]);
               } else {
                 uint4 u;
                 u.x = pack_bf16x2(f[0], f[1]);
                 u.y = pack_bf16x2(f[2], f[3]);
                 u.z = pack_bf16x2(f[4], f[5]);
                 u.w = pack_bf16x2(f[6], f[7]);
-                *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + off + n) = u;
+                *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + o + n) = u;
               }
             } else {
               // ragged N tail (e.g. conv_out, N = 4): scalar path
-              for (int i = 0; i < 8 && n + i < p.N; ++i) {
-                float x = f[i];
-                if (p.bias) x += p.bias[n + i];
-                if (rv) x += __bfloat162float(rv[n + i]);
-                if (p.residual) x += __bfloat162float(p.residual[off + n + i]);
+              for (int e = 0; e < 8 && n + e < p.N; ++e) {
+                float x = f[e];
+                if (p.bias) x += p.bias[n + e];
+                if (rv) x += __bfloat162float(rv[n + e]);
+                if (p.residual) x += __bfloat162float(p.residual[o + n + e]);
                 if (p.act == 1) x = silu_f(x);
                 if (p.out_fp32) {
                   if (p.round_bf16) x = __bfloat162float(__float2bfloat16_rn(x));
-                  reinterpret_cast<float*>(p.out)[off + n + i] = x;
+                  reinterpret_cast<float*>(p.out)[o + n + e] = x;
                 } else {
-                  reinterpret_cast<bf16*>(p.out)[off + n + i] = __float2bfloat16_rn(x);
+                  reinterpret_cast<bf16*>(p.out)[o + n + e] = __float2bfloat16_rn(x);
                 }
               }
             }
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -472,7 +514,7 @@ static int launch_gemm(const pcm_gemm_desc* d, cudaStream_t stream) {
   p.tiles_n = (d->N + d->block_n - 1) / d->block_n;
   p.num_kblocks = nkb;
   const int stage_bytes = kATileBytes + d->block_n * 128;
-  int S = (200 * 1024) / stage_bytes;
+  int S = (kSmemLimit - 1024 - kStagingBytes) / stage_bytes;
   if (S > kMaxStages) S = kMaxStages;
   if (S < 2) return set_error("pcm_gemm: tile too large for shared memory");
   p.num_stages = S;
@@ -489,11 +531,11 @@ static int launch_gemm(const pcm_gemm_desc* d, cudaStream_t stream) {
   p.alpha = d->alpha;
   p.act = d->act;
 
-  const size_t smem = static_cast<size_t>(S) * stage_bytes + 1024;
+  const size_t smem = static_cast<size_t>(S) * stage_bytes + kStagingBytes + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     CUDA_TRY(cudaFuncSetAttribute(pcm_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  220 * 1024));
+                                  kSmemLimit));
     attr_set = true;
   }
   const int tiles = p.tiles_m * p.tiles_n;
