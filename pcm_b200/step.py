@@ -54,12 +54,11 @@ class PCMTrainStep:
         B = batch
         self.coef = torch.zeros(B, 16, device=device, dtype=torch.float64)
         self.start_t, self.t, self.end_t = (torch.zeros(B, **i64) for _ in range(3))
-        self.noisy = torch.zeros(B, height, width, 4, **f32)
-        self.x_prev = torch.zeros_like(self.noisy)
-        self.d_eps = torch.zeros_like(self.noisy)
+        self.x_prev = torch.zeros(B, height, width, 4, **f32)
+        self.d_eps = torch.zeros_like(self.x_prev)
         self.loss = torch.zeros(1, **f32)
-        self.model_pred = torch.zeros_like(self.noisy) if keep_debug else None
-        self.target = torch.zeros_like(self.noisy) if keep_debug else None
+        self.model_pred = torch.zeros_like(self.x_prev) if keep_debug else None
+        self.target = torch.zeros_like(self.x_prev) if keep_debug else None
         n = self.unet.lora_master.numel()
         self.exp_avg = torch.zeros(n, **f32)
         self.exp_avg_sq = torch.zeros(n, **f32)
@@ -71,8 +70,14 @@ class PCMTrainStep:
         self.in_noise = torch.zeros_like(self.in_latents)
         self.in_index = torch.zeros(B, **i64)
         self.in_w = torch.zeros(B, **f32)
-        self.in_prompt = torch.zeros(B * 77, cfg.cross_attention_dim, device=device, dtype=BF16)
-        self.in_uncond = torch.zeros_like(self.in_prompt)
+        # prompt and uncond embeddings are the two halves of ONE buffer so that the two teacher
+        # passes of the CFG solve (T15:1219-1244) run as a single batch-2B forward
+        self.in_ctx2 = torch.zeros(2 * B * 77, cfg.cross_attention_dim, device=device, dtype=BF16)
+        self.in_prompt = self.in_ctx2[:B * 77]
+        self.in_uncond = self.in_ctx2[B * 77:]
+        self.noisy2 = torch.zeros(2 * B, height, width, 4, **f32)
+        self.noisy = self.noisy2[:B]
+        self.start_t2 = torch.zeros(2 * B, **i64)
         self.graph = None
 
     def set_lr(self, lr):
@@ -88,8 +93,17 @@ class PCMTrainStep:
         ops._call("pcm_add_noise", self.in_latents.data_ptr(), self.in_noise.data_ptr(), self.coef.data_ptr(),
                   per, B, self.bf16_mode, self.noisy.data_ptr())
         eps_s = u.forward(self.noisy, self.start_t, self.in_prompt, lora=True, save=True)
-        eps_c = u.forward(self.noisy, self.start_t, self.in_prompt, lora=False)
-        eps_u = u.forward(self.noisy, self.start_t, self.in_uncond, lora=False) if self.apply_cfg else eps_c
+        if self.apply_cfg:
+            # cond + uncond teacher passes batched: same frozen weights, 2B samples
+            ops._call("pcm_add_noise", self.in_latents.data_ptr(), self.in_noise.data_ptr(),
+                      self.coef.data_ptr(), per, B, self.bf16_mode, self.noisy2[B:].data_ptr())
+            self.start_t2[:B].copy_(self.start_t)
+            self.start_t2[B:].copy_(self.start_t)
+            eps_cu = u.forward(self.noisy2, self.start_t2, self.in_ctx2, lora=False)
+            eps_c, eps_u = eps_cu[:B], eps_cu[B:]
+        else:
+            eps_c = u.forward(self.noisy, self.start_t, self.in_prompt, lora=False)
+            eps_u = eps_c
         ops._call("pcm_teacher_step", eps_c.data_ptr(), eps_u.data_ptr(), self.noisy.data_ptr(),
                   self.coef.data_ptr(), per, B, self.x_prev.data_ptr())
         eps_t = u.forward(self.x_prev, self.t, self.in_prompt, lora=True)
