@@ -235,10 +235,14 @@ class UNetRef:
         q = q.view(B, S, H, d).transpose(1, 2)
         k = k.view(B, k.shape[1], H, d).transpose(1, 2)
         v = v.view(B, v.shape[1], H, d).transpose(1, 2)
-        s = (q @ k.transpose(-1, -2)) * (d ** -0.5)
-        p = torch.softmax(s, dim=-1)
-        p = _q(p, self.emu)  # the flash kernels feed bf16 probabilities to the PV product
-        o = (p @ v).transpose(1, 2).reshape(B, S, Cc)
+        outs = []
+        blk = 1024 if (S > 1024 and not torch.is_grad_enabled()) else S   # bound the S x S scratch
+        for i in range(0, S, blk):
+            s = (q[:, :, i:i + blk] @ k.transpose(-1, -2)) * (d ** -0.5)
+            p = torch.softmax(s, dim=-1)
+            p = _q(p, self.emu)  # the flash kernels feed bf16 probabilities to the PV product
+            outs.append(p @ v)
+        o = (outs[0] if len(outs) == 1 else torch.cat(outs, dim=2)).transpose(1, 2).reshape(B, S, Cc)
         return _q(o, self.emu)
 
     # -- blocks -----------------------------------------------------------------------------

@@ -199,6 +199,28 @@ pcm_gemm_kernel(const __grid_constant__ GemmParams p) {
       const int nchunks = p.block_n >> 5;
       for (int j = 0; j < nchunks; ++j, ++chunk_ctr) {
         float* sb = stg + (chunk_ctr & 1) * (128 * 32);
+        const int n = n0 + j * 32 + cg * 8;
+        const bool full8 = n + 8 <= p.N;
+        // Issue every global read of this chunk's phase 2 up front (bias, row vectors, residual):
+        // their latency overlaps the TMEM load / staging / barrier, and nothing is re-read after a
+        // store (out may alias residual for in-place accumulation, each element by the same thread).
+        float4 bia0 = make_float4(0.f, 0.f, 0.f, 0.f), bia1 = bia0;
+        uint4 rres[4], rrv[4];
+        if (full8) {
+          if (p.bias) {
+            bia0 = *reinterpret_cast<const float4*>(p.bias + n);
+            bia1 = *reinterpret_cast<const float4*>(p.bias + n + 4);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            rres[i] = make_uint4(0, 0, 0, 0);
+            rrv[i] = make_uint4(0, 0, 0, 0);
+            if (valid[i]) {
+              if (p.residual) rres[i] = *reinterpret_cast<const uint4*>(p.residual + off[i] + n);
+              if (rvp[i]) rrv[i] = *reinterpret_cast<const uint4*>(rvp[i] + n);
+            }
+          }
+        }
         {
           uint32_t v[32];
           tmem_ld_32x32(taddr + j * 32, v);
@@ -219,7 +241,6 @@ pcm_gemm_kernel(const __grid_constant__ GemmParams p) {
           }
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        const int n = n0 + j * 32 + cg * 8;
         if (n < p.N) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -232,29 +253,19 @@ pcm_gemm_kernel(const __grid_constant__ GemmParams p) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) f[e] *= p.alpha;
             const long long o = off[i];
-            const bf16* rv = rvp[i];
-            if (n + 8 <= p.N) {
-              if (p.bias) {
-                const float4 b0 = *reinterpret_cast<const float4*>(p.bias + n);
-                const float4 b1 = *reinterpret_cast<const float4*>(p.bias + n + 4);
-                f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-                f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-              }
-              if (rv) {
-                const uint4 u = *reinterpret_cast<const uint4*>(rv + n);
+            if (full8) {
+              f[0] += bia0.x; f[1] += bia0.y; f[2] += bia0.z; f[3] += bia0.w;
+              f[4] += bia1.x; f[5] += bia1.y; f[6] += bia1.z; f[7] += bia1.w;
+              {
                 float2 t;
-                t = unpack_bf16x2(u.x); f[0] += t.x; f[1] += t.y;
-                t = unpack_bf16x2(u.y); f[2] += t.x; f[3] += t.y;
-                t = unpack_bf16x2(u.z); f[4] += t.x; f[5] += t.y;
-                t = unpack_bf16x2(u.w); f[6] += t.x; f[7] += t.y;
-              }
-              if (p.residual) {
-                const uint4 u = *reinterpret_cast<const uint4*>(p.residual + o + n);
-                float2 t;
-                t = unpack_bf16x2(u.x); f[0] += t.x; f[1] += t.y;
-                t = unpack_bf16x2(u.y); f[2] += t.x; f[3] += t.y;
-                t = unpack_bf16x2(u.z); f[4] += t.x; f[5] += t.y;
-                t = unpack_bf16x2(u.w); f[6] += t.x; f[7] += t.y;
+                t = unpack_bf16x2(rrv[i].x); f[0] += t.x; f[1] += t.y;
+                t = unpack_bf16x2(rrv[i].y); f[2] += t.x; f[3] += t.y;
+                t = unpack_bf16x2(rrv[i].z); f[4] += t.x; f[5] += t.y;
+                t = unpack_bf16x2(rrv[i].w); f[6] += t.x; f[7] += t.y;
+                t = unpack_bf16x2(rres[i].x); f[0] += t.x; f[1] += t.y;
+                t = unpack_bf16x2(rres[i].y); f[2] += t.x; f[3] += t.y;
+                t = unpack_bf16x2(rres[i].z); f[4] += t.x; f[5] += t.y;
+                t = unpack_bf16x2(rres[i].w); f[6] += t.x; f[7] += t.y;
               }
               if (p.act == 1) {
 #pragma unroll
@@ -278,6 +289,7 @@ pcm_gemm_kernel(const __grid_constant__ GemmParams p) {
               }
             } else {
               // ragged N tail (e.g. conv_out, N = 4): scalar path
+              const bf16* rv = rvp[i];
               for (int e = 0; e < 8 && n + e < p.N; ++e) {
                 float x = f[e];
                 if (p.bias) x += p.bias[n + e];
