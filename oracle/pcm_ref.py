@@ -134,7 +134,10 @@ def pcm_step_ref(cfg, params, batch, *, multiphase, num_ddim=50, loss_type="hube
     inf = torch.from_numpy(inference_indices(num_ddim, multiphase)).long()    # T15:1157-1163
     c_skip_s, c_out_s = [append_dims(x, 4) for x in scalings_for_boundary_conditions_online(index, inf)]
     c_skip, c_out = [append_dims(x, 4) for x in scalings_for_boundary_conditions_target(index, inf)]
-    noisy = rq(add_noise(ac, latents, noise, start_t))                        # T15:1178
+    if emulate_bf16:   # latents are weight_dtype (bf16) tensors in the reference: run its exact op sequence
+        noisy = add_noise(ac, latents.bfloat16(), noise.bfloat16(), start_t).float()
+    else:
+        noisy = add_noise(ac, latents, noise, start_t)                        # T15:1178
     w4 = rq(w.reshape(-1, 1, 1, 1))                                           # T15:1183-1185
 
     eps = student(noisy, start_t, prompt)                                     # T15:1192-1198

@@ -135,8 +135,11 @@ __global__ void upsample2x_bwd_kernel(const bf16* __restrict__ dout, int B, int 
 __global__ void conv3x3_c4_kernel(const float* __restrict__ in, int B, int H, int W, int C,
                                   const bf16* __restrict__ w, const float* __restrict__ bias,
                                   int sgn, int round_in, bf16* __restrict__ out) {
-  extern __shared__ float s_w[];  // [C][36]
-  for (int i = threadIdx.x; i < C * 36; i += blockDim.x) s_w[i] = __bfloat162float(w[i]);
+  extern __shared__ float s_w[];  // [36][C]: consecutive threads read consecutive channels
+  for (int i = threadIdx.x; i < C * 36; i += blockDim.x) {
+    const int ch = i / 36, k = i - ch * 36;
+    s_w[k * C + ch] = __bfloat162float(w[i]);
+  }
   __syncthreads();
   const int nvec = C >> 3;
   const long long total = static_cast<long long>(B) * H * W * nvec;
@@ -166,10 +169,14 @@ __global__ void conv3x3_c4_kernel(const float* __restrict__ in, int B, int H, in
           t.z = __bfloat162float(__float2bfloat16_rn(t.z));
           t.w = __bfloat162float(__float2bfloat16_rn(t.w));
         }
+        const float tin[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float* ww = s_w + (cv * 8 + i) * 36 + (kh * 3 + kw) * 4;
-          acc[i] += t.x * ww[0] + t.y * ww[1] + t.z * ww[2] + t.w * ww[3];
+        for (int k = 0; k < 4; ++k) {
+          const float* ww = s_w + ((kh * 3 + kw) * 4 + k) * C + cv * 8;
+          const float4 w0 = *reinterpret_cast<const float4*>(ww);
+          const float4 w1 = *reinterpret_cast<const float4*>(ww + 4);
+          acc[0] += tin[k] * w0.x; acc[1] += tin[k] * w0.y; acc[2] += tin[k] * w0.z; acc[3] += tin[k] * w0.w;
+          acc[4] += tin[k] * w1.x; acc[5] += tin[k] * w1.y; acc[6] += tin[k] * w1.z; acc[7] += tin[k] * w1.w;
         }
       }
     }

@@ -74,46 +74,66 @@ __global__ void gn_stats_kernel(const bf16* __restrict__ x1, const bf16* __restr
   }
 }
 
-// out = [silu]( (x - mean) * rstd * gamma + beta ), bf16
+// out = [silu]( (x - mean) * rstd * gamma + beta ), bf16.  Same thread -> channel-vector mapping as
+// gn_stats_kernel: each thread folds the statistics of its 8 channels into (scale, shift) once and
+// then streams pixels (16-byte load, 8 FMAs, 16-byte store), two pixels in flight.
 __global__ void gn_apply_kernel(const bf16* __restrict__ x1, const bf16* __restrict__ x2, int C1,
-                                int C2, int HW, int G, long long total_vec,
+                                int C2, int HW, int G, int pix_per_block,
                                 const float* __restrict__ stats, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, float eps, int silu,
                                 bf16* __restrict__ out) {
   const int C = C1 + C2;
+  const int b = blockIdx.y;
   const int nvec = C >> 3;
+  const int tx = threadIdx.x % nvec, ty = threadIdx.x / nvec;
+  const int ny = blockDim.x / nvec;
   const int cpg = C / G;
   const float inv_n = 1.f / (static_cast<float>(HW) * cpg);
-  for (long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; v < total_vec;
-       v += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long pix = v / nvec;
-    const int c = static_cast<int>(v - pix * nvec) * 8;
-    const int b = static_cast<int>(pix / HW);
-    const uint4 u = *reinterpret_cast<const uint4*>(gn_src(x1, x2, C1, C2, pix, c));
-    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-    float f[8];
+  const int c = tx * 8;
+  float sc[8], sh[8];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float2 t = unpack_bf16x2(w[i]);
-      f[2 * i] = t.x;
-      f[2 * i + 1] = t.y;
-    }
+  for (int i = 0; i < 8; ++i) {
+    const int g = (c + i) / cpg;
+    const float mean = stats[(b * G + g) * 2] * inv_n;
+    const float var = fmaxf(stats[(b * G + g) * 2 + 1] * inv_n - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + eps);
+    sc[i] = rstd * gamma[c + i];
+    sh[i] = beta[c + i] - mean * sc[i];
+  }
+  const int p0 = blockIdx.x * pix_per_block;
+  const int p1 = min(HW, p0 + pix_per_block);
+  for (int p = p0 + ty; p < p1; p += 2 * ny) {
+    const long long pixa = static_cast<long long>(b) * HW + p;
+    const bool two = p + ny < p1;
+    const long long pixb = pixa + ny;
+    const uint4 ua = *reinterpret_cast<const uint4*>(gn_src(x1, x2, C1, C2, pixa, c));
+    uint4 ub = make_uint4(0, 0, 0, 0);
+    if (two) ub = *reinterpret_cast<const uint4*>(gn_src(x1, x2, C1, C2, pixb, c));
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int g = (c + i) / cpg;
-      const float mean = stats[(b * G + g) * 2] * inv_n;
-      const float var = fmaxf(stats[(b * G + g) * 2 + 1] * inv_n - mean * mean, 0.f);
-      const float rstd = rsqrtf(var + eps);
-      float y = (f[i] - mean) * rstd * gamma[c + i] + beta[c + i];
-      if (silu) y = silu_f(y);
-      f[i] = y;
+    for (int h = 0; h < 2; ++h) {
+      if (h == 1 && !two) break;
+      const uint4 u = h == 0 ? ua : ub;
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+      float f[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 t = unpack_bf16x2(w[i]);
+        f[2 * i] = t.x;
+        f[2 * i + 1] = t.y;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float y = f[i] * sc[i] + sh[i];
+        if (silu) y = silu_f(y);
+        f[i] = y;
+      }
+      uint4 o;
+      o.x = pack_bf16x2(f[0], f[1]);
+      o.y = pack_bf16x2(f[2], f[3]);
+      o.z = pack_bf16x2(f[4], f[5]);
+      o.w = pack_bf16x2(f[6], f[7]);
+      *reinterpret_cast<uint4*>(out + (h == 0 ? pixa : pixb) * C + c) = o;
     }
-    uint4 o;
-    o.x = pack_bf16x2(f[0], f[1]);
-    o.y = pack_bf16x2(f[2], f[3]);
-    o.z = pack_bf16x2(f[4], f[5]);
-    o.w = pack_bf16x2(f[6], f[7]);
-    *reinterpret_cast<uint4*>(out + pix * C + c) = o;
   }
 }
 
@@ -194,23 +214,38 @@ __global__ void gn_bwd_stats_kernel(const bf16* __restrict__ dy, const bf16* __r
 }
 
 // dx = rstd * (gamma*dyh - (s1 + xhat*s2)/n) (+ add); written to dx1 (first C1 channels) and
-// dx2 (remaining C2 channels).
+// dx2 (remaining C2 channels).  Per-thread channel constants hoisted like gn_apply_kernel.
 __global__ void gn_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x1,
                                     const bf16* __restrict__ x2, int C1, int C2, int HW, int G,
-                                    long long total_vec, const float* __restrict__ stats,
+                                    int pix_per_block, const float* __restrict__ stats,
                                     const float* __restrict__ red, const float* __restrict__ gamma,
                                     const float* __restrict__ beta, float eps, int silu,
                                     const bf16* __restrict__ add, bf16* __restrict__ dx1,
                                     bf16* __restrict__ dx2) {
   const int C = C1 + C2;
+  const int b = blockIdx.y;
   const int nvec = C >> 3;
+  const int tx = threadIdx.x % nvec, ty = threadIdx.x / nvec;
+  const int ny = blockDim.x / nvec;
   const int cpg = C / G;
   const float inv_n = 1.f / (static_cast<float>(HW) * cpg);
-  for (long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; v < total_vec;
-       v += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long pix = v / nvec;
-    const int c = static_cast<int>(v - pix * nvec) * 8;
-    const int b = static_cast<int>(pix / HW);
+  const int c = tx * 8;
+  float mean[8], rstd[8], gm[8], bt[8], s1[8], s2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int g = (c + i) / cpg;
+    mean[i] = stats[(b * G + g) * 2] * inv_n;
+    const float var = fmaxf(stats[(b * G + g) * 2 + 1] * inv_n - mean[i] * mean[i], 0.f);
+    rstd[i] = rsqrtf(var + eps);
+    gm[i] = gamma[c + i];
+    bt[i] = beta[c + i];
+    s1[i] = red[(b * G + g) * 2] * inv_n;
+    s2[i] = red[(b * G + g) * 2 + 1] * inv_n;
+  }
+  const int p0 = blockIdx.x * pix_per_block;
+  const int p1 = min(HW, p0 + pix_per_block);
+  for (int p = p0 + ty; p < p1; p += ny) {
+    const long long pix = static_cast<long long>(b) * HW + p;
     const uint4 u = *reinterpret_cast<const uint4*>(gn_src(x1, x2, C1, C2, pix, c));
     const uint4 d = *reinterpret_cast<const uint4*>(dy + pix * C + c);
     uint4 ad = make_uint4(0, 0, 0, 0);
@@ -228,18 +263,11 @@ __global__ void gn_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __r
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         const int k = 2 * i + j;
-        const int g = (c + k) / cpg;
-        const float mean = stats[(b * G + g) * 2] * inv_n;
-        const float var = fmaxf(stats[(b * G + g) * 2 + 1] * inv_n - mean * mean, 0.f);
-        const float rstd = rsqrtf(var + eps);
-        const float gmk = gamma[c + k];
-        const float xh = (xs[j] - mean) * rstd;
+        const float xh = (xs[j] - mean[k]) * rstd[k];
         float gg = ds[j];
-        if (silu) gg *= dsilu_f(xh * gmk + beta[c + k]);
-        gg *= gmk;
-        const float s1 = red[(b * G + g) * 2] * inv_n;
-        const float s2 = red[(b * G + g) * 2 + 1] * inv_n;
-        o[k] = rstd * (gg - s1 - xh * s2) + as[j];
+        if (silu) gg *= dsilu_f(xh * gm[k] + bt[k]);
+        gg *= gm[k];
+        o[k] = rstd[k] * (gg - s1[k] - xh * s2[k]) + as[j];
       }
     }
     uint4 ov;
@@ -415,13 +443,9 @@ extern "C" int pcm_groupnorm_fwd(const void* x1, const void* x2, int C1, int C2,
   gn_stats_kernel<<<dim3(nblk, B), threads, 0, stream>>>(
       reinterpret_cast<const bf16*>(x1), reinterpret_cast<const bf16*>(x2), C1, C2, HW, G, ppb,
       stats);
-  const long long total_vec = static_cast<long long>(B) * HW * (C / 8);
-  int grid = static_cast<int>((total_vec + 255) / 256);
-  if (grid > num_sms() * 16) grid = num_sms() * 16;
-  gn_apply_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const bf16*>(x1),
-                                            reinterpret_cast<const bf16*>(x2), C1, C2, HW, G,
-                                            total_vec, stats, gamma, beta, eps, silu,
-                                            reinterpret_cast<bf16*>(out));
+  gn_apply_kernel<<<dim3(nblk, B), threads, 0, stream>>>(
+      reinterpret_cast<const bf16*>(x1), reinterpret_cast<const bf16*>(x2), C1, C2, HW, G, ppb, stats,
+      gamma, beta, eps, silu, reinterpret_cast<bf16*>(out));
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -438,14 +462,10 @@ extern "C" int pcm_groupnorm_bwd(const void* dy, const void* x1, const void* x2,
   gn_bwd_stats_kernel<<<dim3(nblk, B), threads, 0, stream>>>(
       reinterpret_cast<const bf16*>(dy), reinterpret_cast<const bf16*>(x1),
       reinterpret_cast<const bf16*>(x2), C1, C2, HW, G, ppb, stats, gamma, beta, eps, silu, red);
-  const long long total_vec = static_cast<long long>(B) * HW * (C / 8);
-  int grid = static_cast<int>((total_vec + 255) / 256);
-  if (grid > num_sms() * 16) grid = num_sms() * 16;
-  gn_bwd_apply_kernel<<<grid, 256, 0, stream>>>(
+  gn_bwd_apply_kernel<<<dim3(nblk, B), threads, 0, stream>>>(
       reinterpret_cast<const bf16*>(dy), reinterpret_cast<const bf16*>(x1),
-      reinterpret_cast<const bf16*>(x2), C1, C2, HW, G, total_vec, stats, red, gamma, beta, eps,
-      silu, reinterpret_cast<const bf16*>(add), reinterpret_cast<bf16*>(dx1),
-      reinterpret_cast<bf16*>(dx2));
+      reinterpret_cast<const bf16*>(x2), C1, C2, HW, G, ppb, stats, red, gamma, beta, eps, silu,
+      reinterpret_cast<const bf16*>(add), reinterpret_cast<bf16*>(dx1), reinterpret_cast<bf16*>(dx2));
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

@@ -102,8 +102,13 @@ __global__ void pcm_add_noise_kernel(const float* __restrict__ x, const float* _
       xv = rbf(xv);
       nv = rbf(nv);
     }
-    float y = static_cast<float>(c[kNoiseA]) * xv + static_cast<float>(c[kNoiseS]) * nv;
-    if (bf16_mode) y = rbf(y);
+    float y;
+    if (bf16_mode) {
+      // the reference evaluates add_noise on bf16 tensors: every op rounds (S15:513-523)
+      y = rbf(rbf(static_cast<float>(c[kNoiseA]) * xv) + rbf(static_cast<float>(c[kNoiseS]) * nv));
+    } else {
+      y = static_cast<float>(c[kNoiseA]) * xv + static_cast<float>(c[kNoiseS]) * nv;
+    }
     out[i] = y;
   }
 }

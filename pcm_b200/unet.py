@@ -125,7 +125,7 @@ class UNetB200:
             A = self.lora_master[lo.a_off:lo.a_off + self.r * taps * L.cin]
             Bm = self.lora_master[lo.b_off:lo.b_off + L.cout * self.r]
             if L.kind == "conv":
-                out[L.name + ".lora_A.weight"] = A.view(self.r, L.k, L.k, L.cin).permute(0, 3, 1, 2).contiguous()
+                out[L.name + ".lora_A.weight"] = A.view(self.r, L.k, L.k, L.cin).permute(0, 3, 1, 2).clone()
                 out[L.name + ".lora_B.weight"] = Bm.view(L.cout, self.r, 1, 1).clone()
             else:
                 out[L.name + ".lora_A.weight"] = A.view(self.r, L.cin).clone()
@@ -137,7 +137,7 @@ class UNetB200:
         for L in self.lora_layers:
             lo = L.lora
             if L.kind == "conv":
-                out[L.name + ".lora_A.weight"] = lo.gA.view(self.r, L.k, L.k, L.cin).permute(0, 3, 1, 2).contiguous()
+                out[L.name + ".lora_A.weight"] = lo.gA.view(self.r, L.k, L.k, L.cin).permute(0, 3, 1, 2).clone()
                 out[L.name + ".lora_B.weight"] = lo.gB.view(L.cout, self.r, 1, 1).clone()
             else:
                 out[L.name + ".lora_A.weight"] = lo.gA.clone()
