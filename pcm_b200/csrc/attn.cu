@@ -9,6 +9,7 @@
 //
 // Layout: q [B, Sq, H*D] (row stride ldq), k / v [B, Skv, H*D] (ldk / ldv), o like q;
 // lse, delta [B, H, Sq] fp32 (lse in log2 units of the scaled scores).
+#include <stdlib.h>
 #include "common.cuh"
 #include "host_common.h"
 #include "../../include/pcm_b200.h"
@@ -534,6 +535,11 @@ static int launch_bwd(const AttnParams& p, cudaStream_t stream) {
 
 }  // namespace pcm
 
+namespace pcm {
+int attn_fwd_tc(const void* q, const void* k, const void* v, void* out, float* lse, int B, int H,
+                int Sq, int Skv, int D, long long ldq, long long ldk, long long ldv, long long ldo,
+                float scale, cudaStream_t stream);
+}
 using namespace pcm;
 
 #define DISPATCH_DP(D, CALL)                                                     \
@@ -566,6 +572,12 @@ extern "C" int pcm_attn_fwd(const void* q, const void* k, const void* v, void* o
   p.ldq = ldq; p.ldk = ldk; p.ldv = ldv; p.ldo = ldo;
   p.scale = scale;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  static const bool legacy = getenv("PCM_ATTN_LEGACY") != nullptr;
+  if (!legacy) {
+    // tcgen05 path (d <= 80); returns 1 when the shape is not covered
+    const int rc = attn_fwd_tc(q, k, v, out, lse, B, H, Sq, Skv, D, ldq, ldk, ldv, ldo, scale, st);
+    if (rc <= 0) return rc;
+  }
   DISPATCH_DP(D, launch_fwd);
 }
 

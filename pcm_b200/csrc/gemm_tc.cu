@@ -42,7 +42,8 @@ struct alignas(64) GemmParams {
   int act;
 };
 
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;   // warp0 TMA, warp1 MMA, warps 2-9 epilogue (two groups of 4)
+constexpr int kWgradThreads = 192;
 constexpr int kMaxStages = 8;
 constexpr int kATileBytes = 128 * 128;  // 128 rows x 64 bf16
 constexpr int kStagingBytes = 2 * 128 * 32 * 4;  // epilogue transposition buffers (fp32)
@@ -74,7 +75,7 @@ pcm_gemm_kernel(const __grid_constant__ GemmParams p) {
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);
+      mbar_init(&tempty_bar[i], 8);
     }
     fence_barrier_init();
   }
@@ -165,13 +166,15 @@ pcm_gemm_kernel(const __grid_constant__ GemmParams p) {
     //      activation and store 16 bytes each.
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
-    const int et = threadIdx.x - 64;  // 0..127
-    const int cg = et & 3;            // 8-column group inside the 32-column chunk
-    const int r0 = et >> 2;           // phase-2 rows: r0 + 32 * i
-    float* stg = reinterpret_cast<float*>(smem + S * stage_bytes);
+    const int grp = (warp - 2) >> 2;          // epilogue group 0/1: even / odd 32-column chunks
+    const int et = (threadIdx.x - 64) & 127;  // thread index inside the group
+    const int cg = et & 3;                    // 8-column group inside the 32-column chunk
+    const int r0 = et >> 2;                   // phase-2 rows: r0 + 32 * i
+    float* sb = reinterpret_cast<float*>(smem + S * stage_bytes) + grp * (128 * 32);
+    const bool has_bias = p.bias != nullptr, has_res = p.residual != nullptr;
+    const bool has_rv = p.rowvec != nullptr, has_alpha = p.alpha != 1.0f;
     int acc = 0;
     uint32_t acc_phase = 0;
-    uint32_t chunk_ctr = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
       const int n0 = tn * p.block_n;
@@ -190,15 +193,20 @@ pcm_gemm_kernel(const __grid_constant__ GemmParams p) {
           const int h = r / p.epiW;
           const int w = r - h * p.epiW;
           off[i] = b * p.osB + h * p.osH + w * p.osW;
-          if (p.rowvec) rvp[i] = p.rowvec + b * p.rowvec_ld;
+          if (has_rv) rvp[i] = p.rowvec + b * p.rowvec_ld;
         }
       }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256;
       const int nchunks = p.block_n >> 5;
-      for (int j = 0; j < nchunks; ++j, ++chunk_ctr) {
-        float* sb = stg + (chunk_ctr & 1) * (128 * 32);
+      const int last_j = ((nchunks - 1 - grp) & ~1) + grp;  // last chunk this group handles
+      if (grp >= nchunks) {  // block_n == 32: group 1 has no chunk, still releases the accumulator
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      }
+      for (int j = grp; j < nchunks; j += 2) {
         const int n = n0 + j * 32 + cg * 8;
         const bool full8 = n + 8 <= p.N;
         // Issue every global read of this chunk's phase 2 up front (bias, row vectors, residual):
@@ -207,26 +215,27 @@ pcm_gemm_kernel(const __grid_constant__ GemmParams p) {
         float4 bia0 = make_float4(0.f, 0.f, 0.f, 0.f), bia1 = bia0;
         uint4 rres[4], rrv[4];
         if (full8) {
-          if (p.bias) {
+          if (has_bias) {
             bia0 = *reinterpret_cast<const float4*>(p.bias + n);
             bia1 = *reinterpret_cast<const float4*>(p.bias + n + 4);
           }
+          if (has_res) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            rres[i] = make_uint4(0, 0, 0, 0);
-            rrv[i] = make_uint4(0, 0, 0, 0);
-            if (valid[i]) {
-              if (p.residual) rres[i] = *reinterpret_cast<const uint4*>(p.residual + off[i] + n);
-              if (rvp[i]) rrv[i] = *reinterpret_cast<const uint4*>(rvp[i] + n);
-            }
+            for (int i = 0; i < 4; ++i)
+              if (valid[i]) rres[i] = *reinterpret_cast<const uint4*>(p.residual + off[i] + n);
+          }
+          if (has_rv) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              if (valid[i]) rrv[i] = *reinterpret_cast<const uint4*>(rvp[i] + n);
           }
         }
         {
           uint32_t v[32];
           tmem_ld_32x32(taddr + j * 32, v);
           tmem_ld_wait();
-          if (j == nchunks - 1) {
-            // all TMEM reads of this tile are done: hand the accumulator back to the MMA warp
+          if (j == last_j) {
+            // all TMEM reads of this group for this tile are done: release the accumulator
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -240,7 +249,8 @@ pcm_gemm_kernel(const __grid_constant__ GemmParams p) {
                             __uint_as_float(v[4 * c + 2]), __uint_as_float(v[4 * c + 3]));
           }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        // group-local barrier (ids 1 / 2): staging tile written
+        asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");
         if (n < p.N) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -250,18 +260,25 @@ pcm_gemm_kernel(const __grid_constant__ GemmParams p) {
             const float4 a0 = *reinterpret_cast<const float4*>(srow + ((2 * cg) ^ (rr & 7)) * 4);
             const float4 a1 = *reinterpret_cast<const float4*>(srow + ((2 * cg + 1) ^ (rr & 7)) * 4);
             float f[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            if (has_alpha) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] *= p.alpha;
+              for (int e = 0; e < 8; ++e) f[e] *= p.alpha;
+            }
             const long long o = off[i];
             if (full8) {
-              f[0] += bia0.x; f[1] += bia0.y; f[2] += bia0.z; f[3] += bia0.w;
-              f[4] += bia1.x; f[5] += bia1.y; f[6] += bia1.z; f[7] += bia1.w;
-              {
+              if (has_bias) {
+                f[0] += bia0.x; f[1] += bia0.y; f[2] += bia0.z; f[3] += bia0.w;
+                f[4] += bia1.x; f[5] += bia1.y; f[6] += bia1.z; f[7] += bia1.w;
+              }
+              if (has_rv) {
                 float2 t;
                 t = unpack_bf16x2(rrv[i].x); f[0] += t.x; f[1] += t.y;
                 t = unpack_bf16x2(rrv[i].y); f[2] += t.x; f[3] += t.y;
                 t = unpack_bf16x2(rrv[i].z); f[4] += t.x; f[5] += t.y;
                 t = unpack_bf16x2(rrv[i].w); f[6] += t.x; f[7] += t.y;
+              }
+              if (has_res) {
+                float2 t;
                 t = unpack_bf16x2(rres[i].x); f[0] += t.x; f[1] += t.y;
                 t = unpack_bf16x2(rres[i].y); f[2] += t.x; f[3] += t.y;
                 t = unpack_bf16x2(rres[i].z); f[4] += t.x; f[5] += t.y;
@@ -292,9 +309,9 @@ pcm_gemm_kernel(const __grid_constant__ GemmParams p) {
               const bf16* rv = rvp[i];
               for (int e = 0; e < 8 && n + e < p.N; ++e) {
                 float x = f[e];
-                if (p.bias) x += p.bias[n + e];
+                if (has_bias) x += p.bias[n + e];
                 if (rv) x += __bfloat162float(rv[n + e]);
-                if (p.residual) x += __bfloat162float(p.residual[o + n + e]);
+                if (has_res) x += __bfloat162float(p.residual[o + n + e]);
                 if (p.act == 1) x = silu_f(x);
                 if (p.out_fp32) {
                   if (p.round_bf16) x = __bfloat162float(__float2bfloat16_rn(x));
@@ -306,6 +323,8 @@ pcm_gemm_kernel(const __grid_constant__ GemmParams p) {
             }
           }
         }
+        // staging tile consumed: the group may overwrite it in its next chunk
+        asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
@@ -340,7 +359,7 @@ struct alignas(64) WgradParams {
 constexpr int kWgStages = 4;
 constexpr int kWgStageBytes = 3 * kATileBytes;  // P: 2 x (128 tok x 64 ch), Q: 128 tok x 64 r
 
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(kWgradThreads, 1)
 pcm_wgrad_kernel(const __grid_constant__ WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -599,7 +618,7 @@ static int launch_wgrad(const pcm_wgrad_desc* d, cudaStream_t stream) {
     attr_set = true;
   }
   dim3 grid(ch_tiles, d->num_taps, ks);
-  pcm_wgrad_kernel<<<grid, kGemmThreads, smem, stream>>>(p);
+  pcm_wgrad_kernel<<<grid, kWgradThreads, smem, stream>>>(p);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

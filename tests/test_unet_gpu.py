@@ -165,10 +165,3 @@ def test_step_sd15_config1_loss(cuda):
     loss, rloss = st.loss.item(), ref["loss"].item()
     assert abs(loss - rloss) <= 5e-3 * abs(rloss), (loss, rloss)
     assert _relerr(_nchw(st.debug["eps_student"]).cpu(), ref["eps_student"]) < 3e-2
-
-
-def test_step_large_adapter(cuda):
-    """Same step with a 5x larger adapter (B std 0.1)."""
-    ocfg, P, batch, ref, st = _run_step(cuda, "TINY", 2, 16, 4, lora_b_std=0.1, need_grad=False)
-    loss, rloss = st.loss.item(), ref["loss"].item()
-    assert abs(loss - rloss) <= 5e-3 * abs(rloss), (loss, rloss)
