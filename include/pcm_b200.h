@@ -104,6 +104,7 @@ int pcm_groupnorm_fwd(const void* x1, const void* x2, int C1, int C2, int B, int
 int pcm_groupnorm_bwd(const void* dy, const void* x1, const void* x2, int C1, int C2, int B, int HW,
                       int G, const float* gamma, const float* beta, float eps, int silu,
                       const float* stats, float* red, const void* add, void* dx1, void* dx2,
+                      float* colsum /* optional fp32 [B, C]: per-image column sums of dx */,
                       void* stream);
 /* stats: [M, 2] (mean, rstd) */
 int pcm_layernorm_fwd(const void* x, int M, int C, const float* gamma, const float* beta, float eps,
@@ -133,6 +134,7 @@ int pcm_conv3x3_c4(const float* in, int B, int H, int W, int C, const void* w, c
 int pcm_timestep_embed(const int64_t* t, int B, int C, void* out, void* stream);
 int pcm_colsum(const void* x, int B, int HW, int C, void* out, void* stream);
 int pcm_add_bf16(const void* a, const void* b, int64_t n, void* out, void* stream);
+int pcm_cast_f32_bf16(const float* in, int64_t n, void* out, void* stream);
 
 /* ---- PCM solver arithmetic (fused; fp32 latents, batch outermost, `per` elements/sample) ---
  * coef: [B, 16] doubles (internal layout, see csrc/pcm_ops.cu). */

@@ -93,6 +93,7 @@ EXPORTS = [
     "pcm_timestep_embed",
     "pcm_colsum",
     "pcm_add_bf16",
+    "pcm_cast_f32_bf16",
     "pcm_prepare",
     "pcm_add_noise",
     "pcm_teacher_step",
@@ -110,7 +111,7 @@ ARGTYPES = {
     "pcm_gemm": [P, P],
     "pcm_wgrad": [P, P],
     "pcm_groupnorm_fwd": [P, P, I, I, I, I, I, P, P, F, I, P, P, P],
-    "pcm_groupnorm_bwd": [P, P, P, I, I, I, I, I, P, P, F, I, P, P, P, P, P, P],
+    "pcm_groupnorm_bwd": [P, P, P, I, I, I, I, I, P, P, F, I, P, P, P, P, P, P, P],
     "pcm_layernorm_fwd": [P, I, I, P, P, F, P, P, P],
     "pcm_layernorm_bwd": [P, P, I, I, P, P, P, P, P],
     "pcm_attn_fwd": [P, P, P, P, P, I, I, I, I, I, L64, L64, L64, L64, F, P],
@@ -123,6 +124,7 @@ ARGTYPES = {
     "pcm_timestep_embed": [P, I, I, P, P],
     "pcm_colsum": [P, I, I, I, P, P],
     "pcm_add_bf16": [P, P, L64, P, P],
+    "pcm_cast_f32_bf16": [P, L64, P, P],
     "pcm_prepare": [P, I, I, P, I, P, P, I, I, P, P, P, P, P],
     "pcm_add_noise": [P, P, P, L64, I, I, P, P],
     "pcm_teacher_step": [P, P, P, P, L64, I, P, P],

@@ -242,6 +242,12 @@ __global__ void add_bf16_kernel(const bf16* __restrict__ a, const bf16* __restri
   }
 }
 
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ in, long long n, bf16* __restrict__ out) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    out[i] = __float2bfloat16_rn(in[i]);
+}
+
 static inline int ew_grid(long long total, int threads) {
   long long g = (total + threads - 1) / threads;
   const long long cap = static_cast<long long>(num_sms()) * 16;
@@ -317,6 +323,11 @@ extern "C" int pcm_colsum(const void* x, int B, int HW, int C, void* out, void* 
 extern "C" int pcm_add_bf16(const void* a, const void* b, int64_t n, void* out, void* stream) {
   if (n % 8) return set_error("add: n % 8 != 0");
   add_bf16_kernel<<<ew_grid(n / 8, 256), 256, 0, ST(stream)>>>(CBF(a), CBF(b), n / 8, BF(out));
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+extern "C" int pcm_cast_f32_bf16(const float* in, int64_t n, void* out, void* stream) {
+  cast_f32_bf16_kernel<<<ew_grid(n, 256), 256, 0, ST(stream)>>>(in, n, BF(out));
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

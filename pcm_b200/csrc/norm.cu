@@ -221,7 +221,8 @@ __global__ void gn_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __r
                                     const float* __restrict__ red, const float* __restrict__ gamma,
                                     const float* __restrict__ beta, float eps, int silu,
                                     const bf16* __restrict__ add, bf16* __restrict__ dx1,
-                                    bf16* __restrict__ dx2) {
+                                    bf16* __restrict__ dx2, float* __restrict__ colsum) {
+  __shared__ float s_cs[kGnMaxC];
   const int C = C1 + C2;
   const int b = blockIdx.y;
   const int nvec = C >> 3;
@@ -230,6 +231,11 @@ __global__ void gn_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __r
   const int cpg = C / G;
   const float inv_n = 1.f / (static_cast<float>(HW) * cpg);
   const int c = tx * 8;
+  if (colsum) {
+    for (int i = threadIdx.x; i < C; i += blockDim.x) s_cs[i] = 0.f;
+    __syncthreads();
+  }
+  float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   float mean[8], rstd[8], gm[8], bt[8], s1[8], s2[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -279,27 +285,48 @@ __global__ void gn_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __r
       *reinterpret_cast<uint4*>(dx1 + pix * C1 + c) = ov;
     else
       *reinterpret_cast<uint4*>(dx2 + pix * C2 + (c - C1)) = ov;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) cs[k] += o[k];
+  }
+  if (colsum) {  // per-image column sums of dx (time-embedding gradient), fp32
+#pragma unroll
+    for (int k = 0; k < 8; ++k) atomicAdd(&s_cs[c + k], cs[k]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&colsum[b * C + i], s_cs[i]);
   }
 }
 
 // ------------------------------------------------------------------------------------------
-// LayerNorm over the channel dimension, one warp per token row (C <= 1280, C % 8 == 0)
+// LayerNorm over the channel dimension.  LPR lanes cooperate on one token row (C/8 <= 5 * LPR
+// 16-byte vectors, 5 independent loads per lane), 32 / LPR rows per warp; group reductions by
+// xor-shuffles below LPR.  SD1.5: C = 320 / 640 / 1280 -> LPR = 8 / 16 / 32, perfectly balanced.
 // ------------------------------------------------------------------------------------------
-constexpr int kLnMaxVec = 5;  // per lane: C/8/32 <= 5
+constexpr int kLnMaxVec = 5;
 
+template <int LPR>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int LPR>
 __global__ void ln_fwd_kernel(const bf16* __restrict__ x, int M, int C,
                               const float* __restrict__ gamma, const float* __restrict__ beta,
                               float eps, bf16* __restrict__ out, float* __restrict__ stats) {
+  constexpr int RPW = 32 / LPR;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (warp >= M) return;
+  const int sub = lane % LPR;
+  const int r = warp * RPW + lane / LPR;
+  const bool rvalid = r < M;
   const int nvec = C >> 3;
-  const bf16* row = x + static_cast<long long>(warp) * C;
+  const bf16* row = x + static_cast<long long>(rvalid ? r : 0) * C;
   float f[kLnMaxVec][8];
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < kLnMaxVec; ++i) {
-    const int v = lane + i * 32;
+    const int v = sub + i * LPR;
     if (v < nvec) {
       const uint4 u = *reinterpret_cast<const uint4*>(row + v * 8);
       const uint32_t w[4] = {u.x, u.y, u.z, u.w};
@@ -312,11 +339,11 @@ __global__ void ln_fwd_kernel(const bf16* __restrict__ x, int M, int C,
       }
     }
   }
-  const float mean = warp_sum(s) / C;
+  const float mean = group_sum<LPR>(s) / C;
   float ss = 0.f;
 #pragma unroll
   for (int i = 0; i < kLnMaxVec; ++i) {
-    const int v = lane + i * 32;
+    const int v = sub + i * LPR;
     if (v < nvec) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -325,20 +352,26 @@ __global__ void ln_fwd_kernel(const bf16* __restrict__ x, int M, int C,
       }
     }
   }
-  const float rstd = rsqrtf(warp_sum(ss) / C + eps);
-  if (lane == 0 && stats) {
-    stats[warp * 2] = mean;
-    stats[warp * 2 + 1] = rstd;
+  const float rstd = rsqrtf(group_sum<LPR>(ss) / C + eps);
+  if (!rvalid) return;
+  if (sub == 0 && stats) {
+    stats[r * 2] = mean;
+    stats[r * 2 + 1] = rstd;
   }
-  bf16* orow = out + static_cast<long long>(warp) * C;
+  bf16* orow = out + static_cast<long long>(r) * C;
 #pragma unroll
   for (int i = 0; i < kLnMaxVec; ++i) {
-    const int v = lane + i * 32;
+    const int v = sub + i * LPR;
     if (v < nvec) {
+      const float4 g0 = *reinterpret_cast<const float4*>(gamma + v * 8);
+      const float4 g1 = *reinterpret_cast<const float4*>(gamma + v * 8 + 4);
+      const float4 b0 = *reinterpret_cast<const float4*>(beta + v * 8);
+      const float4 b1 = *reinterpret_cast<const float4*>(beta + v * 8 + 4);
+      const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
       float o[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        o[j] = (f[i][j] - mean) * rstd * gamma[v * 8 + j] + beta[v * 8 + j];
+      for (int j = 0; j < 8; ++j) o[j] = (f[i][j] - mean) * rstd * gm[j] + bt[j];
       uint4 u;
       u.x = pack_bf16x2(o[0], o[1]);
       u.y = pack_bf16x2(o[2], o[3]);
@@ -350,23 +383,30 @@ __global__ void ln_fwd_kernel(const bf16* __restrict__ x, int M, int C,
 }
 
 // dx = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat)) (+ add)
+template <int LPR>
 __global__ void ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, int M, int C,
                               const float* __restrict__ gamma, const float* __restrict__ stats,
                               const bf16* __restrict__ add, bf16* __restrict__ dx) {
+  constexpr int RPW = 32 / LPR;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (warp >= M) return;
+  const int sub = lane % LPR;
+  const int r = warp * RPW + lane / LPR;
+  const bool rvalid = r < M;
   const int nvec = C >> 3;
-  const long long base = static_cast<long long>(warp) * C;
-  const float mean = stats[warp * 2], rstd = stats[warp * 2 + 1];
+  const long long base = static_cast<long long>(rvalid ? r : 0) * C;
+  const float mean = stats[(rvalid ? r : 0) * 2], rstd = stats[(rvalid ? r : 0) * 2 + 1];
   float g[kLnMaxVec][8], xh[kLnMaxVec][8];
   float s1 = 0.f, s2 = 0.f;
 #pragma unroll
   for (int i = 0; i < kLnMaxVec; ++i) {
-    const int v = lane + i * 32;
+    const int v = sub + i * LPR;
     if (v < nvec) {
       const uint4 u = *reinterpret_cast<const uint4*>(x + base + v * 8);
       const uint4 d = *reinterpret_cast<const uint4*>(dy + base + v * 8);
+      const float4 g0 = *reinterpret_cast<const float4*>(gamma + v * 8);
+      const float4 g1 = *reinterpret_cast<const float4*>(gamma + v * 8 + 4);
+      const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
       const uint32_t w[4] = {u.x, u.y, u.z, u.w};
       const uint32_t dw[4] = {d.x, d.y, d.z, d.w};
 #pragma unroll
@@ -375,18 +415,19 @@ __global__ void ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restric
         const float2 df = unpack_bf16x2(dw[j]);
         xh[i][2 * j] = (xf.x - mean) * rstd;
         xh[i][2 * j + 1] = (xf.y - mean) * rstd;
-        g[i][2 * j] = df.x * gamma[v * 8 + 2 * j];
-        g[i][2 * j + 1] = df.y * gamma[v * 8 + 2 * j + 1];
+        g[i][2 * j] = df.x * gm[2 * j];
+        g[i][2 * j + 1] = df.y * gm[2 * j + 1];
         s1 += g[i][2 * j] + g[i][2 * j + 1];
         s2 += g[i][2 * j] * xh[i][2 * j] + g[i][2 * j + 1] * xh[i][2 * j + 1];
       }
     }
   }
-  s1 = warp_sum(s1) / C;
-  s2 = warp_sum(s2) / C;
+  s1 = group_sum<LPR>(s1) / C;
+  s2 = group_sum<LPR>(s2) / C;
+  if (!rvalid) return;
 #pragma unroll
   for (int i = 0; i < kLnMaxVec; ++i) {
-    const int v = lane + i * 32;
+    const int v = sub + i * LPR;
     if (v < nvec) {
       float o[8];
       float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -410,6 +451,13 @@ __global__ void ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restric
       *reinterpret_cast<uint4*>(dx + base + v * 8) = u;
     }
   }
+}
+
+static inline int ln_lpr(int C) {
+  const int nvec = C / 8;
+  if (nvec <= 8 * kLnMaxVec) return 8;
+  if (nvec <= 16 * kLnMaxVec) return 16;
+  return 32;
 }
 
 static int gn_launch_cfg(int C, int HW, int B, int* threads, int* ppb, int* nblk) {
@@ -453,19 +501,22 @@ extern "C" int pcm_groupnorm_fwd(const void* x1, const void* x2, int C1, int C2,
 extern "C" int pcm_groupnorm_bwd(const void* dy, const void* x1, const void* x2, int C1, int C2,
                                  int B, int HW, int G, const float* gamma, const float* beta,
                                  float eps, int silu, const float* stats, float* red,
-                                 const void* add, void* dx1, void* dx2, void* stream_) {
+                                 const void* add, void* dx1, void* dx2, float* colsum,
+                                 void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   const int C = C1 + C2;
   int threads, ppb, nblk;
   if (int rc = gn_launch_cfg(C, HW, B, &threads, &ppb, &nblk)) return rc;
   CUDA_TRY(cudaMemsetAsync(red, 0, sizeof(float) * 2 * B * G, stream));
+  if (colsum) CUDA_TRY(cudaMemsetAsync(colsum, 0, sizeof(float) * B * C, stream));
   gn_bwd_stats_kernel<<<dim3(nblk, B), threads, 0, stream>>>(
       reinterpret_cast<const bf16*>(dy), reinterpret_cast<const bf16*>(x1),
       reinterpret_cast<const bf16*>(x2), C1, C2, HW, G, ppb, stats, gamma, beta, eps, silu, red);
   gn_bwd_apply_kernel<<<dim3(nblk, B), threads, 0, stream>>>(
       reinterpret_cast<const bf16*>(dy), reinterpret_cast<const bf16*>(x1),
       reinterpret_cast<const bf16*>(x2), C1, C2, HW, G, ppb, stats, red, gamma, beta, eps, silu,
-      reinterpret_cast<const bf16*>(add), reinterpret_cast<bf16*>(dx1), reinterpret_cast<bf16*>(dx2));
+      reinterpret_cast<const bf16*>(add), reinterpret_cast<bf16*>(dx1), reinterpret_cast<bf16*>(dx2),
+      colsum);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -475,9 +526,14 @@ extern "C" int pcm_layernorm_fwd(const void* x, int M, int C, const float* gamma
                                  void* stream_) {
   if (C % 8 != 0 || C > kLnMaxVec * 256) return set_error("layernorm: unsupported C");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  const int wpb = 8;
-  ln_fwd_kernel<<<(M + wpb - 1) / wpb, wpb * 32, 0, stream>>>(
-      reinterpret_cast<const bf16*>(x), M, C, gamma, beta, eps, reinterpret_cast<bf16*>(out), stats);
+  const int wpb = 8, lpr = ln_lpr(C);
+  const int rows_per_block = wpb * (32 / lpr);
+  const int grid = (M + rows_per_block - 1) / rows_per_block;
+  const bf16* xp = reinterpret_cast<const bf16*>(x);
+  bf16* op = reinterpret_cast<bf16*>(out);
+  if (lpr == 8) ln_fwd_kernel<8><<<grid, wpb * 32, 0, stream>>>(xp, M, C, gamma, beta, eps, op, stats);
+  else if (lpr == 16) ln_fwd_kernel<16><<<grid, wpb * 32, 0, stream>>>(xp, M, C, gamma, beta, eps, op, stats);
+  else ln_fwd_kernel<32><<<grid, wpb * 32, 0, stream>>>(xp, M, C, gamma, beta, eps, op, stats);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -486,10 +542,15 @@ extern "C" int pcm_layernorm_bwd(const void* dy, const void* x, int M, int C, co
                                  const float* stats, const void* add, void* dx, void* stream_) {
   if (C % 8 != 0 || C > kLnMaxVec * 256) return set_error("layernorm: unsupported C");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  const int wpb = 8;
-  ln_bwd_kernel<<<(M + wpb - 1) / wpb, wpb * 32, 0, stream>>>(
-      reinterpret_cast<const bf16*>(dy), reinterpret_cast<const bf16*>(x), M, C, gamma, stats,
-      reinterpret_cast<const bf16*>(add), reinterpret_cast<bf16*>(dx));
+  const int wpb = 8, lpr = ln_lpr(C);
+  const int rows_per_block = wpb * (32 / lpr);
+  const int grid = (M + rows_per_block - 1) / rows_per_block;
+  const bf16 *dyp = reinterpret_cast<const bf16*>(dy), *xp = reinterpret_cast<const bf16*>(x);
+  const bf16* ap = reinterpret_cast<const bf16*>(add);
+  bf16* dxp = reinterpret_cast<bf16*>(dx);
+  if (lpr == 8) ln_bwd_kernel<8><<<grid, wpb * 32, 0, stream>>>(dyp, xp, M, C, gamma, stats, ap, dxp);
+  else if (lpr == 16) ln_bwd_kernel<16><<<grid, wpb * 32, 0, stream>>>(dyp, xp, M, C, gamma, stats, ap, dxp);
+  else ln_bwd_kernel<32><<<grid, wpb * 32, 0, stream>>>(dyp, xp, M, C, gamma, stats, ap, dxp);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

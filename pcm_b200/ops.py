@@ -178,11 +178,16 @@ def groupnorm_fwd(x1, x2, gamma, beta, eps, silu, out, stats, B, HW, G=32):
     return out
 
 
-def groupnorm_bwd(dy, x1, x2, gamma, beta, eps, silu, stats, red, add, dx1, dx2, B, HW, G=32):
+def groupnorm_bwd(dy, x1, x2, gamma, beta, eps, silu, stats, red, add, dx1, dx2, B, HW, G=32, colsum=None):
     C1 = x1.shape[-1]
     C2 = x2.shape[-1] if x2 is not None else 0
     _call("pcm_groupnorm_bwd", _p(dy), _p(x1), _p(x2), C1, C2, B, HW, G, _p(gamma), _p(beta), eps,
-          int(silu), _p(stats), _p(red), _p(add), _p(dx1), _p(dx2))
+          int(silu), _p(stats), _p(red), _p(add), _p(dx1), _p(dx2), _p(colsum))
+
+
+def cast_f32_bf16(x, out):
+    _call("pcm_cast_f32_bf16", _p(x), x.numel(), _p(out))
+    return out
 
 
 def layernorm_fwd(x, gamma, beta, out, stats, eps=1e-5):

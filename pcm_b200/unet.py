@@ -476,14 +476,14 @@ class UNetB200:
                          out_strides=(plane.stride(2), plane.stride(1), plane.stride(0)), epi=(Wo, Wo * Ho))
         return dx
 
-    def gn_bwd(self, rec, dy, add=None):
+    def gn_bwd(self, rec, dy, add=None, colsum=None):
         _, name, xs, stats, eps, silu, B, HW = rec
         L = self.layers[name]
         dx1 = torch.empty_like(xs[0])
         dx2 = torch.empty_like(xs[1]) if len(xs) > 1 else None
         red = self._new(B, self.cfg.norm_num_groups, 2, dtype=torch.float32)
         ops.groupnorm_bwd(dy, xs[0], xs[1] if len(xs) > 1 else None, L.gamma, L.beta, eps, silu, stats, red,
-                          add, dx1, dx2, B, HW, self.cfg.norm_num_groups)
+                          add, dx1, dx2, B, HW, self.cfg.norm_num_groups, colsum=colsum)
         return dx1, dx2
 
     def ln_bwd(self, rec, dy, add=None):
@@ -513,10 +513,12 @@ class UNetB200:
         B, H, W, cout = dout.shape
         M = B * H * W
         dh2 = self.conv3_bwd(conv2, dout)                              # grad wrt silu(gn2(h1))
-        dh1, _ = self.gn_bwd(gn2, dh2.view(M, cout))                   # grad wrt h1 [M, cout]
-        # time embedding branch: d tproj[b, n] = sum_hw dh1
+        # grad wrt h1 [M, cout]; its per-image column sums (= d tproj[b, n], the time-embedding
+        # branch) are accumulated by the same kernel
+        cs32 = self._new(B, cout, dtype=torch.float32)
+        dh1, _ = self.gn_bwd(gn2, dh2.view(M, cout), colsum=cs32)
         drow = self._new(B, cout)
-        ops.colsum(dh1, drow, B, H * W)
+        ops.cast_f32_bf16(cs32, drow)
         self.linear_bwd(tlin, drow, need_dx=False)
         dh = self.conv3_bwd(conv1, dh1.view(B, H, W, cout), need_dx=need_dx)
         dsc = self.linear_bwd(recs[4], dout.view(M, cout), need_dx=need_dx) if has_sc else dout.view(M, cout)
