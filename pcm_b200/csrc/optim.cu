@@ -68,44 +68,81 @@ __global__ void state_step_kernel(float* state) { state[1] += 1.f; }
 
 // LoRA refresh table entry: masters A [r][taps][cin] and B [n][r] (fp32, offsets in elements)
 struct RefreshEntry {
-  long long a_off, b_off;          // into the fp32 master buffer
+  long long a_off, b_off;              // into the fp32 master buffer
   long long a_fwd, sb_fwd, sb_t, a_t;  // into the bf16 operand buffer
   int cin, taps, n, r;
-  long long work_begin;            // prefix sum of per-entry work items
+  long long work_begin;                // prefix sum of per-entry 64x64 tiles (A tiles, then B tiles)
 };
 
-// work item space per entry: [0, r*taps*cin) -> A element; then [.., + n*r) -> B element
-__global__ void lora_refresh_kernel(const float* __restrict__ master,
-                                    const RefreshEntry* __restrict__ tab, int num_entries,
-                                    long long total_work, float scale, bf16* __restrict__ opnd) {
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total_work;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    // binary search for the entry
+// One block per 64x64 fp32 tile (r = 64): coalesced read, bf16 copy in the source layout, and the
+// transposed copy through shared memory so both writes are 128-byte contiguous per row.
+//   A tile (rows r, columns [c0, c0+64) of tap t): a_fwd[r][t*cin + c]  and  a_t[c][t*64 + r]
+//   B tile (rows n0.., columns r):                 sb_fwd[n][r] = s*B   and  sb_t[r][n]
+__global__ void __launch_bounds__(256) lora_refresh_kernel(const float* __restrict__ master,
+                                                           const RefreshEntry* __restrict__ tab,
+                                                           int num_entries, float scale,
+                                                           bf16* __restrict__ opnd) {
+  __shared__ float tile[64][65];
+  __shared__ RefreshEntry e;
+  __shared__ long long tidx;
+  if (threadIdx.x == 0) {
+    const long long i = blockIdx.x;
     int lo = 0, hi = num_entries - 1;
     while (lo < hi) {
       const int mid = (lo + hi + 1) >> 1;
       if (tab[mid].work_begin <= i) lo = mid; else hi = mid - 1;
     }
-    const RefreshEntry e = tab[lo];
-    long long j = i - e.work_begin;
-    const long long na = static_cast<long long>(e.r) * e.taps * e.cin;
-    if (j < na) {
-      // A[r][t][c]
-      const float val = master[e.a_off + j];
-      const bf16 h = __float2bfloat16_rn(val);
-      opnd[e.a_fwd + j] = h;
-      const int c = static_cast<int>(j % e.cin);
-      const int t = static_cast<int>((j / e.cin) % e.taps);
-      const int rr = static_cast<int>(j / (static_cast<long long>(e.cin) * e.taps));
-      opnd[e.a_t + (static_cast<long long>(c) * e.taps + t) * e.r + rr] = h;  // A^T [c][t][r]
-    } else {
-      j -= na;
-      const float val = master[e.b_off + j] * scale;
-      const bf16 h = __float2bfloat16_rn(val);
-      opnd[e.sb_fwd + j] = h;  // [n][r]
-      const int rr = static_cast<int>(j % e.r);
-      const int nn = static_cast<int>(j / e.r);
-      opnd[e.sb_t + static_cast<long long>(rr) * e.n + nn] = h;  // [r][n]
+    e = tab[lo];
+    tidx = i - tab[lo].work_begin;
+  }
+  __syncthreads();
+  const int ktot = e.taps * e.cin;
+  const long long a_tiles = ktot / 64;
+  const bool is_a = tidx < a_tiles;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // 16 float4 columns x 16 rows
+  if (is_a) {
+    const int c0 = static_cast<int>(tidx) * 64;  // column in [0, taps*cin); one tap per tile
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = ty + 16 * i;
+      const float4 v = *reinterpret_cast<const float4*>(master + e.a_off + static_cast<long long>(r) * ktot + c0 + tx * 4);
+      tile[r][tx * 4] = v.x; tile[r][tx * 4 + 1] = v.y; tile[r][tx * 4 + 2] = v.z; tile[r][tx * 4 + 3] = v.w;
+      uint2 u;
+      u.x = pack_bf16x2(v.x, v.y);
+      u.y = pack_bf16x2(v.z, v.w);
+      *reinterpret_cast<uint2*>(opnd + e.a_fwd + static_cast<long long>(r) * ktot + c0 + tx * 4) = u;
+    }
+    __syncthreads();
+    const int t = c0 / e.cin, cc0 = c0 - t * e.cin;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = ty + 16 * i;  // a_t row (input channel), 64 consecutive r
+      uint2 u;
+      u.x = pack_bf16x2(tile[tx * 4][c], tile[tx * 4 + 1][c]);
+      u.y = pack_bf16x2(tile[tx * 4 + 2][c], tile[tx * 4 + 3][c]);
+      *reinterpret_cast<uint2*>(opnd + e.a_t + (static_cast<long long>(cc0 + c) * e.taps + t) * 64 + tx * 4) = u;
+    }
+  } else {
+    const int n0 = static_cast<int>(tidx - a_tiles) * 64;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int nn = ty + 16 * i;
+      float4 v = *reinterpret_cast<const float4*>(master + e.b_off + static_cast<long long>(n0 + nn) * 64 + tx * 4);
+      v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+      tile[nn][tx * 4] = v.x; tile[nn][tx * 4 + 1] = v.y; tile[nn][tx * 4 + 2] = v.z; tile[nn][tx * 4 + 3] = v.w;
+      uint2 u;
+      u.x = pack_bf16x2(v.x, v.y);
+      u.y = pack_bf16x2(v.z, v.w);
+      *reinterpret_cast<uint2*>(opnd + e.sb_fwd + static_cast<long long>(n0 + nn) * 64 + tx * 4) = u;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = ty + 16 * i;  // sb_t row, 64 consecutive n
+      uint2 u;
+      u.x = pack_bf16x2(tile[tx * 4][r], tile[tx * 4 + 1][r]);
+      u.y = pack_bf16x2(tile[tx * 4 + 2][r], tile[tx * 4 + 3][r]);
+      *reinterpret_cast<uint2*>(opnd + e.sb_t + static_cast<long long>(r) * e.n + n0 + tx * 4) = u;
     }
   }
 }
@@ -141,10 +178,9 @@ extern "C" int pcm_adamw_clip(float* p, float* g, float* m, float* v, int64_t n,
 
 extern "C" int pcm_lora_refresh(const float* master, const void* table, int num_entries,
                                 int64_t total_work, float scale, void* opnd, void* stream) {
-  int grid = static_cast<int>((total_work + 255) / 256);
-  if (grid > num_sms() * 16) grid = num_sms() * 16;
-  lora_refresh_kernel<<<grid, 256, 0, ST(stream)>>>(
-      master, reinterpret_cast<const RefreshEntry*>(table), num_entries, total_work, scale,
+  // total_work = number of 64x64 tiles (r must be 64; cin and n multiples of 64)
+  lora_refresh_kernel<<<static_cast<unsigned>(total_work), 256, 0, ST(stream)>>>(
+      master, reinterpret_cast<const RefreshEntry*>(table), num_entries, scale,
       reinterpret_cast<bf16*>(opnd));
   CUDA_TRY(cudaGetLastError());
   return 0;

@@ -104,7 +104,8 @@ class UNetB200:
                 lo.gB = self.lora_grad[lo.b_off:lo.b_off + nb].view(L.cout, self.r)
                 rows.append([lo.a_off, lo.b_off, a_fwd, sb_fwd, sb_t, a_t, L.cin | (taps << 32),
                              L.cout | (self.r << 32), work])
-                work += na + nb
+                assert self.r == 64 and L.cin % 64 == 0 and L.cout % 64 == 0
+                work += (taps * L.cin) // 64 + L.cout // 64     # 64x64 tiles of A, then of B
             self.refresh_table = torch.tensor(rows, dtype=torch.int64, device=device)
             self.refresh_work = work
             self.refresh_lora()
