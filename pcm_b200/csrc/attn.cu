@@ -92,6 +92,7 @@ constexpr float kLog2e = 1.4426950408889634f;
 // ------------------------------------------------------------------------------------------
 template <int DP>
 __global__ void __launch_bounds__(256) attn_fwd_kernel(const AttnParams p) {
+  griddep_sync();
   constexpr int LDS = DP + 8, BM = 128, BN = 64, T = 256;
   extern __shared__ __align__(16) uint8_t smem_attn[];
   bf16* sQ = reinterpret_cast<bf16*>(smem_attn);
@@ -223,6 +224,7 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const AttnParams p) {
 
 // delta[b,h,s] = sum_d dO * O
 __global__ void attn_delta_kernel(const AttnParams p) {
+  griddep_sync();
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   const long long total = static_cast<long long>(p.B) * p.Sq * p.H;
   if (i >= total) return;
@@ -252,6 +254,7 @@ __global__ void attn_delta_kernel(const AttnParams p) {
 // ------------------------------------------------------------------------------------------
 template <int DP>
 __global__ void __launch_bounds__(128) attn_bwd_dkdv_kernel(const AttnParams p) {
+  griddep_sync();
   constexpr int LDS = DP + 8, BQ = 64, BN = 64, T = 128;
   extern __shared__ __align__(16) uint8_t smem_attn[];
   bf16* sK = reinterpret_cast<bf16*>(smem_attn);
@@ -384,6 +387,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dkdv_kernel(const AttnParams p) 
 // ------------------------------------------------------------------------------------------
 template <int DP>
 __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnParams p) {
+  griddep_sync();
   constexpr int LDS = DP + 8, BQ = 64, BN = 64, T = 128;
   extern __shared__ __align__(16) uint8_t smem_attn[];
   bf16* sQ = reinterpret_cast<bf16*>(smem_attn);
@@ -503,7 +507,7 @@ static int launch_fwd(const AttnParams& p, cudaStream_t stream) {
     set = true;
   }
   dim3 grid((p.Sq + 127) / 128, p.H, p.B);
-  attn_fwd_kernel<DP><<<grid, 256, smem, stream>>>(p);
+  CUDA_TRY(launch_pdl(attn_fwd_kernel<DP>, dim3(grid), dim3(256), smem, stream, p));
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -513,7 +517,7 @@ static int launch_bwd(const AttnParams& p, cudaStream_t stream) {
   constexpr int LDS = DP + 8;
   {
     const long long total = static_cast<long long>(p.B) * p.Sq * p.H;
-    attn_delta_kernel<<<static_cast<int>((total + 127) / 128), 128, 0, stream>>>(p);
+    CUDA_TRY(launch_pdl(attn_delta_kernel, dim3(static_cast<int>((total + 127) / 128)), dim3(128), 0, stream, p));
   }
   const size_t smem1 = static_cast<size_t>(6 * 64) * LDS * sizeof(bf16) + 4 * 64 * sizeof(float);
   const size_t smem2 = static_cast<size_t>(6 * 64) * LDS * sizeof(bf16);
@@ -527,8 +531,8 @@ static int launch_bwd(const AttnParams& p, cudaStream_t stream) {
                                   static_cast<int>(smem2)));
     set = true;
   }
-  attn_bwd_dkdv_kernel<DP><<<dim3((p.Skv + 63) / 64, p.H, p.B), 128, smem1, stream>>>(p);
-  attn_bwd_dq_kernel<DP><<<dim3((p.Sq + 63) / 64, p.H, p.B), 128, smem2, stream>>>(p);
+  CUDA_TRY(launch_pdl(attn_bwd_dkdv_kernel<DP>, dim3(dim3((p.Skv + 63) / 64, p.H, p.B)), dim3(128), smem1, stream, p));
+  CUDA_TRY(launch_pdl(attn_bwd_dq_kernel<DP>, dim3(dim3((p.Sq + 63) / 64, p.H, p.B)), dim3(128), smem2, stream, p));
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

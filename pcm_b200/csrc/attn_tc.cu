@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc_kernel(const __grid
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  griddep_sync();  // PDL: everything above overlapped the previous kernel's tail
   const uint32_t tS = tmem_base;        // S buffers at columns 0 and 128
   const uint32_t tO = tmem_base + 256;  // O tile
 
@@ -331,6 +332,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) attn_fwd_tc2_kernel(const __gri
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  griddep_sync();  // PDL: everything above overlapped the previous kernel's tail
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
@@ -538,7 +540,7 @@ static int launch_tc2(const AttnTcParams& p, cudaStream_t stream) {
     set = true;
   }
   dim3 grid((p.Sq + 255) / 256, p.H, p.B);
-  attn_fwd_tc2_kernel<DP><<<grid, kV2Threads, smem, stream>>>(p);
+  CUDA_TRY(launch_pdl(attn_fwd_tc2_kernel<DP>, dim3(grid), dim3(kV2Threads), smem, stream, p));
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -554,7 +556,7 @@ static int launch_tc(const AttnTcParams& p, cudaStream_t stream) {
     set = true;
   }
   dim3 grid((p.Sq + 127) / 128, p.H, p.B);
-  attn_fwd_tc_kernel<DP><<<grid, kTcThreads, smem, stream>>>(p);
+  CUDA_TRY(launch_pdl(attn_fwd_tc_kernel<DP>, dim3(grid), dim3(kTcThreads), smem, stream, p));
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

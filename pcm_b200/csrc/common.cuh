@@ -24,6 +24,15 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ---------------- programmatic dependent launch (PDL) ----------------
+// Every kernel of this library is launched with programmatic stream serialization: its prologue
+// (barrier init, TMEM allocation, descriptor prefetch) may overlap the tail of the previous kernel.
+// griddep_sync() must be executed before the first global-memory access.
+__device__ __forceinline__ void griddep_sync() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // ---------------- mbarrier ----------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

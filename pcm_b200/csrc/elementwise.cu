@@ -42,6 +42,7 @@ __device__ __forceinline__ float dgelu_erf(float x) {
 // u [M, 2F] -> out [M, F] = u[:, :F] * gelu(u[:, F:])
 __global__ void geglu_fwd_kernel(const bf16* __restrict__ u, long long M, int F,
                                  bf16* __restrict__ out) {
+  griddep_sync();
   const int nvec = F >> 3;
   const long long total = M * nvec;
   for (long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; v < total;
@@ -60,6 +61,7 @@ __global__ void geglu_fwd_kernel(const bf16* __restrict__ u, long long M, int F,
 // du[:, :F] = dgg * gelu(g) ; du[:, F:] = dgg * a * gelu'(g)
 __global__ void geglu_bwd_kernel(const bf16* __restrict__ dgg, const bf16* __restrict__ u,
                                  long long M, int F, bf16* __restrict__ du) {
+  griddep_sync();
   const int nvec = F >> 3;
   const long long total = M * nvec;
   for (long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; v < total;
@@ -83,6 +85,7 @@ __global__ void geglu_bwd_kernel(const bf16* __restrict__ dgg, const bf16* __res
 // nearest 2x: in [B, H, W, C] -> out [B, 2H, 2W, C]
 __global__ void upsample2x_kernel(const bf16* __restrict__ in, int B, int H, int W, int C,
                                   bf16* __restrict__ out) {
+  griddep_sync();
   const int nvec = C >> 3;
   const long long total = static_cast<long long>(B) * 4 * H * W * nvec;
   for (long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; v < total;
@@ -102,6 +105,7 @@ __global__ void upsample2x_kernel(const bf16* __restrict__ in, int B, int H, int
 // gradient of nearest 2x: dout [B, 2H, 2W, C] -> din [B, H, W, C] (sum of the 2x2 block)
 __global__ void upsample2x_bwd_kernel(const bf16* __restrict__ dout, int B, int H, int W, int C,
                                       bf16* __restrict__ din) {
+  griddep_sync();
   const int nvec = C >> 3;
   const long long total = static_cast<long long>(B) * H * W * nvec;
   for (long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; v < total;
@@ -135,6 +139,7 @@ __global__ void upsample2x_bwd_kernel(const bf16* __restrict__ dout, int B, int 
 __global__ void conv3x3_c4_kernel(const float* __restrict__ in, int B, int H, int W, int C,
                                   const bf16* __restrict__ w, const float* __restrict__ bias,
                                   int sgn, int round_in, bf16* __restrict__ out) {
+  griddep_sync();
   extern __shared__ float s_w[];  // [36][C]: consecutive threads read consecutive channels
   for (int i = threadIdx.x; i < C * 36; i += blockDim.x) {
     const int ch = i / 36, k = i - ch * 36;
@@ -187,6 +192,7 @@ __global__ void conv3x3_c4_kernel(const float* __restrict__ in, int B, int H, in
 // get_timestep_embedding(flip_sin_to_cos=True, downscale_freq_shift=0): [cos | sin]
 __global__ void timestep_embed_kernel(const long long* __restrict__ t, int B, int C,
                                       bf16* __restrict__ out) {
+  griddep_sync();
   const int half = C >> 1;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * half) return;
@@ -201,6 +207,7 @@ __global__ void timestep_embed_kernel(const long long* __restrict__ t, int B, in
 
 // out[b, c] = sum over HW rows of x[b, :, c]   (bf16 in, bf16 out, fp32 accumulate)
 __global__ void colsum_kernel(const bf16* __restrict__ x, int HW, int C, bf16* __restrict__ out) {
+  griddep_sync();
   // grid (C/8 vectors / blockDim.x chunks, B); blockDim (32 vectors, 8 row-lanes)
   __shared__ float s[8][32][9];
   const int b = blockIdx.y;
@@ -231,6 +238,7 @@ __global__ void colsum_kernel(const bf16* __restrict__ x, int HW, int C, bf16* _
 
 __global__ void add_bf16_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b,
                                 long long nvec, bf16* __restrict__ out) {
+  griddep_sync();
   for (long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; v < nvec;
        v += static_cast<long long>(gridDim.x) * blockDim.x) {
     float x[8], y[8];
@@ -243,6 +251,7 @@ __global__ void add_bf16_kernel(const bf16* __restrict__ a, const bf16* __restri
 }
 
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ in, long long n, bf16* __restrict__ out) {
+  griddep_sync();
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x)
     out[i] = __float2bfloat16_rn(in[i]);
@@ -265,15 +274,15 @@ using namespace pcm;
 
 extern "C" int pcm_geglu_fwd(const void* u, int64_t M, int F, void* out, void* stream) {
   if (F % 8) return set_error("geglu: F % 8 != 0");
-  geglu_fwd_kernel<<<ew_grid(M * (F / 8), 256), 256, 0, ST(stream)>>>(CBF(u), M, F, BF(out));
+  CUDA_TRY(launch_pdl(geglu_fwd_kernel, dim3(ew_grid(M * (F / 8), 256)), dim3(256), 0, ST(stream), CBF(u), M, F, BF(out)));
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
 extern "C" int pcm_geglu_bwd(const void* dgg, const void* u, int64_t M, int F, void* du,
                              void* stream) {
   if (F % 8) return set_error("geglu: F % 8 != 0");
-  geglu_bwd_kernel<<<ew_grid(M * (F / 8), 256), 256, 0, ST(stream)>>>(CBF(dgg), CBF(u), M, F,
-                                                                       BF(du));
+  CUDA_TRY(launch_pdl(geglu_bwd_kernel, dim3(ew_grid(M * (F / 8), 256)), dim3(256), 0, ST(stream), CBF(dgg), CBF(u), M, F,
+                                                                       BF(du)));
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -281,7 +290,7 @@ extern "C" int pcm_upsample2x_fwd(const void* in, int B, int H, int W, int C, vo
                                   void* stream) {
   if (C % 8) return set_error("upsample: C % 8 != 0");
   const long long total = static_cast<long long>(B) * 4 * H * W * (C / 8);
-  upsample2x_kernel<<<ew_grid(total, 256), 256, 0, ST(stream)>>>(CBF(in), B, H, W, C, BF(out));
+  CUDA_TRY(launch_pdl(upsample2x_kernel, dim3(ew_grid(total, 256)), dim3(256), 0, ST(stream), CBF(in), B, H, W, C, BF(out)));
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -289,8 +298,8 @@ extern "C" int pcm_upsample2x_bwd(const void* dout, int B, int H, int W, int C, 
                                   void* stream) {
   if (C % 8) return set_error("upsample: C % 8 != 0");
   const long long total = static_cast<long long>(B) * H * W * (C / 8);
-  upsample2x_bwd_kernel<<<ew_grid(total, 256), 256, 0, ST(stream)>>>(CBF(dout), B, H, W, C,
-                                                                      BF(din));
+  CUDA_TRY(launch_pdl(upsample2x_bwd_kernel, dim3(ew_grid(total, 256)), dim3(256), 0, ST(stream), CBF(dout), B, H, W, C,
+                                                                      BF(din)));
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -301,33 +310,32 @@ extern "C" int pcm_conv3x3_c4(const float* in, int B, int H, int W, int C, const
   const size_t smem = static_cast<size_t>(C) * 36 * sizeof(float);
   int grid = ew_grid(total, 256);
   if (grid > num_sms() * 4) grid = num_sms() * 4;
-  conv3x3_c4_kernel<<<grid, 256, smem, ST(stream)>>>(in, B, H, W, C, CBF(w), bias, sgn, round_in,
-                                                     BF(out));
+  CUDA_TRY(launch_pdl(conv3x3_c4_kernel, dim3(grid), dim3(256), smem, ST(stream), in, B, H, W, C, CBF(w), bias, sgn, round_in,
+                                                     BF(out)));
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
 extern "C" int pcm_timestep_embed(const int64_t* t, int B, int C, void* out, void* stream) {
   const int n = B * (C / 2);
-  timestep_embed_kernel<<<(n + 127) / 128, 128, 0, ST(stream)>>>(
-      reinterpret_cast<const long long*>(t), B, C, BF(out));
+  CUDA_TRY(launch_pdl(timestep_embed_kernel, dim3((n + 127) / 128), dim3(128), 0, ST(stream), reinterpret_cast<const long long*>(t), B, C, BF(out)));
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
 extern "C" int pcm_colsum(const void* x, int B, int HW, int C, void* out, void* stream) {
   if (C % 8) return set_error("colsum: C % 8 != 0");
   const int nvec = C / 8;
-  colsum_kernel<<<dim3((nvec + 31) / 32, B), dim3(32, 8), 0, ST(stream)>>>(CBF(x), HW, C, BF(out));
+  CUDA_TRY(launch_pdl(colsum_kernel, dim3(dim3((nvec + 31) / 32, B)), dim3(dim3(32, 8)), 0, ST(stream), CBF(x), HW, C, BF(out)));
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
 extern "C" int pcm_add_bf16(const void* a, const void* b, int64_t n, void* out, void* stream) {
   if (n % 8) return set_error("add: n % 8 != 0");
-  add_bf16_kernel<<<ew_grid(n / 8, 256), 256, 0, ST(stream)>>>(CBF(a), CBF(b), n / 8, BF(out));
+  CUDA_TRY(launch_pdl(add_bf16_kernel, dim3(ew_grid(n / 8, 256)), dim3(256), 0, ST(stream), CBF(a), CBF(b), n / 8, BF(out)));
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
 extern "C" int pcm_cast_f32_bf16(const float* in, int64_t n, void* out, void* stream) {
-  cast_f32_bf16_kernel<<<ew_grid(n, 256), 256, 0, ST(stream)>>>(in, n, BF(out));
+  CUDA_TRY(launch_pdl(cast_f32_bf16_kernel, dim3(ew_grid(n, 256)), dim3(256), 0, ST(stream), in, n, BF(out)));
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

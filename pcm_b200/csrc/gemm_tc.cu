@@ -87,6 +87,7 @@ pcm_gemm_kernel(const __grid_constant__ GemmParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  griddep_sync();  // PDL: everything above overlapped the previous kernel's tail
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -397,6 +398,7 @@ pcm_wgrad_kernel(const __grid_constant__ WgradParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  griddep_sync();  // PDL: everything above overlapped the previous kernel's tail
 
   if (warp == 0) {
     if (lane == 0) {
@@ -571,7 +573,7 @@ static int launch_gemm(const pcm_gemm_desc* d, cudaStream_t stream) {
   }
   const int tiles = p.tiles_m * p.tiles_n;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  pcm_gemm_kernel<<<grid, kGemmThreads, smem, stream>>>(p);
+  CUDA_TRY(launch_pdl(pcm_gemm_kernel, dim3(grid), dim3(kGemmThreads), smem, stream, p));
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -618,7 +620,7 @@ static int launch_wgrad(const pcm_wgrad_desc* d, cudaStream_t stream) {
     attr_set = true;
   }
   dim3 grid(ch_tiles, d->num_taps, ks);
-  pcm_wgrad_kernel<<<grid, kWgradThreads, smem, stream>>>(p);
+  CUDA_TRY(launch_pdl(pcm_wgrad_kernel, dim3(grid), dim3(kWgradThreads), smem, stream, p));
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

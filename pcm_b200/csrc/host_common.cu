@@ -1,5 +1,6 @@
 #include "host_common.h"
 #include <stdio.h>
+#include <stdlib.h>
 #include <cudaTypedefs.h>
 #include "../../include/pcm_b200.h"
 
@@ -15,6 +16,11 @@ int set_cuda_error(cudaError_t e, const char* what) {
   snprintf(g_err, sizeof(g_err), "CUDA error %d (%s) at %s", static_cast<int>(e),
            cudaGetErrorString(e), what);
   return -2;
+}
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) v = getenv("PCM_NO_PDL") ? 0 : 1;
+  return v == 1;
 }
 int num_sms() {
   static int n = 0;

@@ -25,6 +25,7 @@ __device__ __forceinline__ const bf16* gn_src(const bf16* x1, const bf16* x2, in
 __global__ void gn_stats_kernel(const bf16* __restrict__ x1, const bf16* __restrict__ x2, int C1,
                                 int C2, int HW, int G, int pix_per_block,
                                 float* __restrict__ stats) {
+  griddep_sync();
   __shared__ float s_sum[kGnMaxC];
   __shared__ float s_sq[kGnMaxC];
   const int C = C1 + C2;
@@ -82,6 +83,7 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ x1, const bf16* __restr
                                 const float* __restrict__ stats, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, float eps, int silu,
                                 bf16* __restrict__ out) {
+  griddep_sync();
   const int C = C1 + C2;
   const int b = blockIdx.y;
   const int nvec = C >> 3;
@@ -143,6 +145,7 @@ __global__ void gn_bwd_stats_kernel(const bf16* __restrict__ dy, const bf16* __r
                                     int pix_per_block, const float* __restrict__ stats,
                                     const float* __restrict__ gamma, const float* __restrict__ beta,
                                     float eps, int silu, float* __restrict__ red) {
+  griddep_sync();
   __shared__ float s_a[kGnMaxC];
   __shared__ float s_b[kGnMaxC];
   const int C = C1 + C2;
@@ -222,6 +225,7 @@ __global__ void gn_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __r
                                     const float* __restrict__ beta, float eps, int silu,
                                     const bf16* __restrict__ add, bf16* __restrict__ dx1,
                                     bf16* __restrict__ dx2, float* __restrict__ colsum) {
+  griddep_sync();
   __shared__ float s_cs[kGnMaxC];
   const int C = C1 + C2;
   const int b = blockIdx.y;
@@ -314,6 +318,7 @@ template <int LPR>
 __global__ void ln_fwd_kernel(const bf16* __restrict__ x, int M, int C,
                               const float* __restrict__ gamma, const float* __restrict__ beta,
                               float eps, bf16* __restrict__ out, float* __restrict__ stats) {
+  griddep_sync();
   constexpr int RPW = 32 / LPR;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -387,6 +392,7 @@ template <int LPR>
 __global__ void ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, int M, int C,
                               const float* __restrict__ gamma, const float* __restrict__ stats,
                               const bf16* __restrict__ add, bf16* __restrict__ dx) {
+  griddep_sync();
   constexpr int RPW = 32 / LPR;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -488,12 +494,10 @@ extern "C" int pcm_groupnorm_fwd(const void* x1, const void* x2, int C1, int C2,
   int threads, ppb, nblk;
   if (int rc = gn_launch_cfg(C, HW, B, &threads, &ppb, &nblk)) return rc;
   CUDA_TRY(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * B * G, stream));
-  gn_stats_kernel<<<dim3(nblk, B), threads, 0, stream>>>(
-      reinterpret_cast<const bf16*>(x1), reinterpret_cast<const bf16*>(x2), C1, C2, HW, G, ppb,
-      stats);
-  gn_apply_kernel<<<dim3(nblk, B), threads, 0, stream>>>(
-      reinterpret_cast<const bf16*>(x1), reinterpret_cast<const bf16*>(x2), C1, C2, HW, G, ppb, stats,
-      gamma, beta, eps, silu, reinterpret_cast<bf16*>(out));
+  CUDA_TRY(launch_pdl(gn_stats_kernel, dim3(dim3(nblk, B)), dim3(threads), 0, stream, reinterpret_cast<const bf16*>(x1), reinterpret_cast<const bf16*>(x2), C1, C2, HW, G, ppb,
+      stats));
+  CUDA_TRY(launch_pdl(gn_apply_kernel, dim3(dim3(nblk, B)), dim3(threads), 0, stream, reinterpret_cast<const bf16*>(x1), reinterpret_cast<const bf16*>(x2), C1, C2, HW, G, ppb, stats,
+      gamma, beta, eps, silu, reinterpret_cast<bf16*>(out)));
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -509,14 +513,12 @@ extern "C" int pcm_groupnorm_bwd(const void* dy, const void* x1, const void* x2,
   if (int rc = gn_launch_cfg(C, HW, B, &threads, &ppb, &nblk)) return rc;
   CUDA_TRY(cudaMemsetAsync(red, 0, sizeof(float) * 2 * B * G, stream));
   if (colsum) CUDA_TRY(cudaMemsetAsync(colsum, 0, sizeof(float) * B * C, stream));
-  gn_bwd_stats_kernel<<<dim3(nblk, B), threads, 0, stream>>>(
-      reinterpret_cast<const bf16*>(dy), reinterpret_cast<const bf16*>(x1),
-      reinterpret_cast<const bf16*>(x2), C1, C2, HW, G, ppb, stats, gamma, beta, eps, silu, red);
-  gn_bwd_apply_kernel<<<dim3(nblk, B), threads, 0, stream>>>(
-      reinterpret_cast<const bf16*>(dy), reinterpret_cast<const bf16*>(x1),
+  CUDA_TRY(launch_pdl(gn_bwd_stats_kernel, dim3(dim3(nblk, B)), dim3(threads), 0, stream, reinterpret_cast<const bf16*>(dy), reinterpret_cast<const bf16*>(x1),
+      reinterpret_cast<const bf16*>(x2), C1, C2, HW, G, ppb, stats, gamma, beta, eps, silu, red));
+  CUDA_TRY(launch_pdl(gn_bwd_apply_kernel, dim3(dim3(nblk, B)), dim3(threads), 0, stream, reinterpret_cast<const bf16*>(dy), reinterpret_cast<const bf16*>(x1),
       reinterpret_cast<const bf16*>(x2), C1, C2, HW, G, ppb, stats, red, gamma, beta, eps, silu,
       reinterpret_cast<const bf16*>(add), reinterpret_cast<bf16*>(dx1), reinterpret_cast<bf16*>(dx2),
-      colsum);
+      colsum));
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -531,9 +533,9 @@ extern "C" int pcm_layernorm_fwd(const void* x, int M, int C, const float* gamma
   const int grid = (M + rows_per_block - 1) / rows_per_block;
   const bf16* xp = reinterpret_cast<const bf16*>(x);
   bf16* op = reinterpret_cast<bf16*>(out);
-  if (lpr == 8) ln_fwd_kernel<8><<<grid, wpb * 32, 0, stream>>>(xp, M, C, gamma, beta, eps, op, stats);
-  else if (lpr == 16) ln_fwd_kernel<16><<<grid, wpb * 32, 0, stream>>>(xp, M, C, gamma, beta, eps, op, stats);
-  else ln_fwd_kernel<32><<<grid, wpb * 32, 0, stream>>>(xp, M, C, gamma, beta, eps, op, stats);
+  if (lpr == 8) CUDA_TRY(launch_pdl(ln_fwd_kernel<8>, dim3(grid), dim3(wpb * 32), 0, stream, xp, M, C, gamma, beta, eps, op, stats));
+  else if (lpr == 16) CUDA_TRY(launch_pdl(ln_fwd_kernel<16>, dim3(grid), dim3(wpb * 32), 0, stream, xp, M, C, gamma, beta, eps, op, stats));
+  else CUDA_TRY(launch_pdl(ln_fwd_kernel<32>, dim3(grid), dim3(wpb * 32), 0, stream, xp, M, C, gamma, beta, eps, op, stats));
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -548,9 +550,9 @@ extern "C" int pcm_layernorm_bwd(const void* dy, const void* x, int M, int C, co
   const bf16 *dyp = reinterpret_cast<const bf16*>(dy), *xp = reinterpret_cast<const bf16*>(x);
   const bf16* ap = reinterpret_cast<const bf16*>(add);
   bf16* dxp = reinterpret_cast<bf16*>(dx);
-  if (lpr == 8) ln_bwd_kernel<8><<<grid, wpb * 32, 0, stream>>>(dyp, xp, M, C, gamma, stats, ap, dxp);
-  else if (lpr == 16) ln_bwd_kernel<16><<<grid, wpb * 32, 0, stream>>>(dyp, xp, M, C, gamma, stats, ap, dxp);
-  else ln_bwd_kernel<32><<<grid, wpb * 32, 0, stream>>>(dyp, xp, M, C, gamma, stats, ap, dxp);
+  if (lpr == 8) CUDA_TRY(launch_pdl(ln_bwd_kernel<8>, dim3(grid), dim3(wpb * 32), 0, stream, dyp, xp, M, C, gamma, stats, ap, dxp));
+  else if (lpr == 16) CUDA_TRY(launch_pdl(ln_bwd_kernel<16>, dim3(grid), dim3(wpb * 32), 0, stream, dyp, xp, M, C, gamma, stats, ap, dxp));
+  else CUDA_TRY(launch_pdl(ln_bwd_kernel<32>, dim3(grid), dim3(wpb * 32), 0, stream, dyp, xp, M, C, gamma, stats, ap, dxp));
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

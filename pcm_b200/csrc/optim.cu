@@ -14,6 +14,7 @@
 namespace pcm {
 
 __global__ void sumsq_kernel(const float* __restrict__ g, long long n, double* __restrict__ out) {
+  griddep_sync();
   __shared__ double s_part[32];
   double acc = 0.0;
   const long long n4 = n >> 2;
@@ -40,6 +41,7 @@ __global__ void adamw_clip_kernel(float* __restrict__ p, float* __restrict__ g,
                                   const float* __restrict__ state, float beta1, float beta2,
                                   float eps, float wd, float max_norm, float inv_world,
                                   const double* __restrict__ sumsq, int zero_grad) {
+  griddep_sync();
   const float lr = state[0];
   const float step = state[1];
   const float norm = static_cast<float>(sqrt(*sumsq)) * inv_world;
@@ -64,7 +66,8 @@ __global__ void adamw_clip_kernel(float* __restrict__ p, float* __restrict__ g,
   }
 }
 
-__global__ void state_step_kernel(float* state) { state[1] += 1.f; }
+__global__ void state_step_kernel(float* state) {
+  griddep_sync(); state[1] += 1.f; }
 
 // LoRA refresh table entry: masters A [r][taps][cin] and B [n][r] (fp32, offsets in elements)
 struct RefreshEntry {
@@ -82,6 +85,7 @@ __global__ void __launch_bounds__(256) lora_refresh_kernel(const float* __restri
                                                            const RefreshEntry* __restrict__ tab,
                                                            int num_entries, float scale,
                                                            bf16* __restrict__ opnd) {
+  griddep_sync();
   __shared__ float tile[64][65];
   __shared__ RefreshEntry e;
   __shared__ long long tidx;
@@ -157,7 +161,7 @@ extern "C" int pcm_grad_sumsq(const float* g, int64_t n, double* out, void* stre
   int grid = static_cast<int>((n / 4 + 255) / 256);
   if (grid > num_sms() * 8) grid = num_sms() * 8;
   if (grid < 1) grid = 1;
-  sumsq_kernel<<<grid, 256, 0, ST(stream)>>>(g, n, out);
+  CUDA_TRY(launch_pdl(sumsq_kernel, dim3(grid), dim3(256), 0, ST(stream), g, n, out));
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -166,12 +170,12 @@ extern "C" int pcm_adamw_clip(float* p, float* g, float* m, float* v, int64_t n,
                               float beta1, float beta2, float eps, float weight_decay,
                               float max_norm, float inv_world, const double* sumsq, int zero_grad,
                               void* stream) {
-  state_step_kernel<<<1, 1, 0, ST(stream)>>>(state);
+  CUDA_TRY(launch_pdl(state_step_kernel, dim3(1), dim3(1), 0, ST(stream), state));
   int grid = static_cast<int>((n + 255) / 256);
   if (grid > num_sms() * 8) grid = num_sms() * 8;
-  adamw_clip_kernel<<<grid, 256, 0, ST(stream)>>>(p, g, m, v, n, state, beta1, beta2, eps,
+  CUDA_TRY(launch_pdl(adamw_clip_kernel, dim3(grid), dim3(256), 0, ST(stream), p, g, m, v, n, state, beta1, beta2, eps,
                                                   weight_decay, max_norm, inv_world, sumsq,
-                                                  zero_grad);
+                                                  zero_grad));
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -179,9 +183,8 @@ extern "C" int pcm_adamw_clip(float* p, float* g, float* m, float* v, int64_t n,
 extern "C" int pcm_lora_refresh(const float* master, const void* table, int num_entries,
                                 int64_t total_work, float scale, void* opnd, void* stream) {
   // total_work = number of 64x64 tiles (r must be 64; cin and n multiples of 64)
-  lora_refresh_kernel<<<static_cast<unsigned>(total_work), 256, 0, ST(stream)>>>(
-      master, reinterpret_cast<const RefreshEntry*>(table), num_entries, scale,
-      reinterpret_cast<bf16*>(opnd));
+  CUDA_TRY(launch_pdl(lora_refresh_kernel, dim3(static_cast<unsigned>(total_work)), dim3(256), 0, ST(stream), master, reinterpret_cast<const RefreshEntry*>(table), num_entries, scale,
+      reinterpret_cast<bf16*>(opnd)));
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

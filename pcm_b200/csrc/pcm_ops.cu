@@ -43,6 +43,7 @@ __global__ void pcm_prepare_kernel(const float* __restrict__ acp, int num_train,
                                    int B, int bf16_mode, double* __restrict__ coef,
                                    long long* __restrict__ start_t, long long* __restrict__ t_out,
                                    long long* __restrict__ end_t) {
+  griddep_sync();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const int ratio = num_train / num_ddim;  // DDIMSolver.step_ratio (T15:291)
@@ -94,6 +95,7 @@ __global__ void pcm_prepare_kernel(const float* __restrict__ acp, int num_train,
 __global__ void pcm_add_noise_kernel(const float* __restrict__ x, const float* __restrict__ noise,
                                      const double* __restrict__ coef, long long per,
                                      long long total, int bf16_mode, float* __restrict__ out) {
+  griddep_sync();
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const double* c = coef + (i / per) * kCoefN;
@@ -118,6 +120,7 @@ __global__ void pcm_teacher_step_kernel(const float* __restrict__ eps_c,
                                         const float* __restrict__ noisy,
                                         const double* __restrict__ coef, long long per,
                                         long long total, float* __restrict__ x_prev) {
+  griddep_sync();
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const double* c = coef + (i / per) * kCoefN;
@@ -140,6 +143,7 @@ __global__ void pcm_loss_kernel(const float* __restrict__ eps_s, const float* __
                                 int loss_type, float huber_c, float* __restrict__ loss_out,
                                 float* __restrict__ d_eps, float* __restrict__ model_pred_out,
                                 float* __restrict__ target_out) {
+  griddep_sync();
   __shared__ double s_part[32];
   double acc = 0.0;
   const double inv_n = 1.0 / static_cast<double>(total);
@@ -189,6 +193,7 @@ __global__ void pcm_noise_travel_kernel(const float* __restrict__ x, const float
                                         const long long* __restrict__ t_cur,
                                         const long long* __restrict__ t_tgt, long long per,
                                         long long total, float* __restrict__ out) {
+  griddep_sync();
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const long long b = i / per;
@@ -202,6 +207,7 @@ __global__ void pcm_noise_travel_kernel(const float* __restrict__ x, const float
 __global__ void pcm_axpby_f64_kernel(const float* __restrict__ x, const float* __restrict__ y,
                                      const double* __restrict__ ca, const double* __restrict__ cb,
                                      long long per, long long total, double* __restrict__ out) {
+  griddep_sync();
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const long long b = i / per;
@@ -224,19 +230,18 @@ extern "C" int pcm_prepare(const float* acp, int num_train, int num_ddim, const 
                            int multiphase, const int64_t* index, const float* w, int B,
                            int bf16_mode, double* coef, int64_t* start_t, int64_t* t,
                            int64_t* end_t, void* stream) {
-  pcm_prepare_kernel<<<(B + 63) / 64, 64, 0, ST(stream)>>>(
-      acp, num_train, num_ddim, reinterpret_cast<const long long*>(inf_idx), multiphase,
+  CUDA_TRY(launch_pdl(pcm_prepare_kernel, dim3((B + 63) / 64), dim3(64), 0, ST(stream), acp, num_train, num_ddim, reinterpret_cast<const long long*>(inf_idx), multiphase,
       reinterpret_cast<const long long*>(index), w, B, bf16_mode, coef,
       reinterpret_cast<long long*>(start_t), reinterpret_cast<long long*>(t),
-      reinterpret_cast<long long*>(end_t));
+      reinterpret_cast<long long*>(end_t)));
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
 extern "C" int pcm_add_noise(const float* x, const float* noise, const double* coef, int64_t per,
                              int B, int bf16_mode, float* out, void* stream) {
   const long long total = per * B;
-  pcm_add_noise_kernel<<<grid_for(total), 256, 0, ST(stream)>>>(x, noise, coef, per, total,
-                                                                bf16_mode, out);
+  CUDA_TRY(launch_pdl(pcm_add_noise_kernel, dim3(grid_for(total)), dim3(256), 0, ST(stream), x, noise, coef, per, total,
+                                                                bf16_mode, out));
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -244,8 +249,8 @@ extern "C" int pcm_teacher_step(const float* eps_c, const float* eps_u, const fl
                                 const double* coef, int64_t per, int B, float* x_prev,
                                 void* stream) {
   const long long total = per * B;
-  pcm_teacher_step_kernel<<<grid_for(total), 256, 0, ST(stream)>>>(eps_c, eps_u, noisy, coef, per,
-                                                                   total, x_prev);
+  CUDA_TRY(launch_pdl(pcm_teacher_step_kernel, dim3(grid_for(total)), dim3(256), 0, ST(stream), eps_c, eps_u, noisy, coef, per,
+                                                                   total, x_prev));
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -254,9 +259,9 @@ extern "C" int pcm_loss(const float* eps_s, const float* eps_t, const float* noi
                         float huber_c, float* loss_out, float* d_eps, float* model_pred,
                         float* target, void* stream) {
   const long long total = per * B;
-  pcm_loss_kernel<<<1, 1024, 0, ST(stream)>>>(eps_s, eps_t, noisy, x_prev, coef, per, total,
+  CUDA_TRY(launch_pdl(pcm_loss_kernel, dim3(1), dim3(1024), 0, ST(stream), eps_s, eps_t, noisy, x_prev, coef, per, total,
                                               loss_type, huber_c, loss_out, d_eps, model_pred,
-                                              target);
+                                              target));
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -264,9 +269,8 @@ extern "C" int pcm_noise_travel(const float* x, const float* noise, const float*
                                 const int64_t* t_cur, const int64_t* t_tgt, int64_t per, int B,
                                 float* out, void* stream) {
   const long long total = per * B;
-  pcm_noise_travel_kernel<<<grid_for(total), 256, 0, ST(stream)>>>(
-      x, noise, acp, reinterpret_cast<const long long*>(t_cur),
-      reinterpret_cast<const long long*>(t_tgt), per, total, out);
+  CUDA_TRY(launch_pdl(pcm_noise_travel_kernel, dim3(grid_for(total)), dim3(256), 0, ST(stream), x, noise, acp, reinterpret_cast<const long long*>(t_cur),
+      reinterpret_cast<const long long*>(t_tgt), per, total, out));
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -274,7 +278,7 @@ extern "C" int pcm_noise_travel(const float* x, const float* noise, const float*
 extern "C" int pcm_axpby_f64(const float* x, const float* y, const double* ca, const double* cb,
                              int64_t per, int B, double* out, void* stream) {
   const long long total = per * B;
-  pcm_axpby_f64_kernel<<<grid_for(total), 256, 0, ST(stream)>>>(x, y, ca, cb, per, total, out);
+  CUDA_TRY(launch_pdl(pcm_axpby_f64_kernel, dim3(grid_for(total)), dim3(256), 0, ST(stream), x, y, ca, cb, per, total, out));
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
