@@ -45,15 +45,26 @@ __global__ void gn_stats_kernel(const bf16* __restrict__ x1, const bf16* __restr
   for (int i = 0; i < 8; ++i) a[i] = q[i] = 0.f;
   if (ty < ny) {
     const int c = tx * 8;
-    for (int p = p0 + ty; p < p1; p += ny) {
-      const long long pix = static_cast<long long>(b) * HW + p;
-      const uint4 u = *reinterpret_cast<const uint4*>(gn_src(x1, x2, C1, C2, pix, c));
-      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    // four independent 16-byte loads in flight per thread
+    for (int p = p0 + ty; p < p1; p += 4 * ny) {
+      uint4 u[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float2 f = unpack_bf16x2(w[i]);
-        a[2 * i] += f.x; q[2 * i] += f.x * f.x;
-        a[2 * i + 1] += f.y; q[2 * i + 1] += f.y * f.y;
+      for (int k = 0; k < 4; ++k) {
+        const int pp = p + k * ny;
+        u[k] = make_uint4(0, 0, 0, 0);
+        if (pp < p1)
+          u[k] = *reinterpret_cast<const uint4*>(
+              gn_src(x1, x2, C1, C2, static_cast<long long>(b) * HW + pp, c));
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = unpack_bf16x2(w[i]);
+          a[2 * i] += f.x; q[2 * i] += f.x * f.x;
+          a[2 * i + 1] += f.y; q[2 * i + 1] += f.y * f.y;
+        }
       }
     }
 #pragma unroll
