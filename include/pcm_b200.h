@@ -65,6 +65,8 @@ typedef struct {
   int32_t out_fp32, round_bf16;
   float alpha;
   int32_t act;           /* 0 none, 1 SiLU applied to the result */
+  int32_t ksplit;        /* > 1: split the K program over ksplit CTAs per tile (small-M, long-K) */
+  void* splitk_ws;       /* fp32 [M, N] scratch for the split-K partial sums (required if ksplit > 1) */
 } pcm_gemm_desc;
 
 /* LoRA weight-gradient descriptor: out[ch, r] += alpha * sum_m P[m(+tap), ch] * Q[m, r], r < 64.

@@ -35,7 +35,7 @@ class GemmDesc(C.Structure):
         ("out", C.c_void_p), ("bias", C.c_void_p), ("rowvec", C.c_void_p), ("residual", C.c_void_p),
         ("osW", C.c_int64), ("osH", C.c_int64), ("osB", C.c_int64), ("rowvec_ld", C.c_int64),
         ("epiW", C.c_int32), ("epiHW", C.c_int32), ("out_fp32", C.c_int32), ("round_bf16", C.c_int32),
-        ("alpha", C.c_float), ("act", C.c_int32),
+        ("alpha", C.c_float), ("act", C.c_int32), ("ksplit", C.c_int32), ("splitk_ws", C.c_void_p),
     ]
 
 

@@ -543,6 +543,10 @@ namespace pcm {
 int attn_fwd_tc(const void* q, const void* k, const void* v, void* out, float* lse, int B, int H,
                 int Sq, int Skv, int D, long long ldq, long long ldk, long long ldv, long long ldo,
                 float scale, cudaStream_t stream);
+int attn_bwd_tc(const void* q, const void* k, const void* v, const void* dout, const float* lse,
+                const float* delta, void* dq, void* dk, void* dv, int B, int H, int Sq, int Skv, int D,
+                long long ldq, long long ldk, long long ldv, long long ldo, float scale,
+                cudaStream_t stream);
 }
 using namespace pcm;
 
@@ -604,5 +608,13 @@ extern "C" int pcm_attn_bwd(const void* q, const void* k, const void* v, const v
   p.ldq = ldq; p.ldk = ldk; p.ldv = ldv; p.ldo = ldo;
   p.scale = scale;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  static const bool legacy = getenv("PCM_ATTN_LEGACY") != nullptr || getenv("PCM_ATTN_BWD_LEGACY") != nullptr;
+  if (!legacy && D <= 64 && D % 8 == 0) {
+    const long long total = static_cast<long long>(B) * Sq * H;
+    CUDA_TRY(launch_pdl(attn_delta_kernel, dim3(static_cast<unsigned>((total + 127) / 128)), dim3(128), 0, st, p));
+    const int rc = attn_bwd_tc(q, k, v, dout, lse, delta, dq, dk, dv, B, H, Sq, Skv, D, ldq, ldk, ldv, ldo,
+                               scale, st);
+    if (rc <= 0) return rc;
+  }
   DISPATCH_DP(D, launch_bwd);
 }

@@ -40,6 +40,8 @@ struct alignas(64) GemmParams {
   int out_fp32, round_bf16;
   float alpha;
   int act;
+  int ksplit;        // > 1: work item = (tile, K split); fp32 partial sums are atomically added
+  float* ws;         // into ws[m * N + n]; bias / residual / activation run in the finalize kernel
 };
 
 constexpr int kGemmThreads = 320;   // warp0 TMA, warp1 MMA, warps 2-9 epilogue (two groups of 4)
@@ -64,7 +66,8 @@ pcm_gemm_kernel(const __grid_constant__ GemmParams p) {
   const int lane = threadIdx.x & 31;
   const int S = p.num_stages;
   const uint32_t stage_bytes = kATileBytes + p.block_n * 128;
-  const int num_tiles = p.tiles_m * p.tiles_n;
+  const int num_items = p.tiles_m * p.tiles_n * p.ksplit;
+  const int kb_per = (p.num_kblocks + p.ksplit - 1) / p.ksplit;
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < PCM_MAX_ASRC; ++i) tma_prefetch_desc(&p.a_maps[i]);
@@ -94,7 +97,9 @@ pcm_gemm_kernel(const __grid_constant__ GemmParams p) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const int tile = item / p.ksplit, ks = item - tile * p.ksplit;
+        const int kb0 = ks * kb_per, kb1 = min(p.num_kblocks, kb0 + kb_per);
         const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
         const int m0 = tm * 128, n0 = tn * p.block_n;
         int b0 = 0, h0 = 0;
@@ -102,9 +107,15 @@ pcm_gemm_kernel(const __grid_constant__ GemmParams p) {
           b0 = m0 / p.geoHW;
           h0 = (m0 - b0 * p.geoHW) / p.geoW;
         }
+        int kidx = 0;
         for (int e = 0; e < p.num_prog; ++e) {
           const KEntry en = p.prog[e];
-          for (int c = 0; c < en.nchunks; ++c) {
+          if (kidx + en.nchunks <= kb0 || kidx >= kb1) {  // entry entirely outside this K split
+            kidx += en.nchunks;
+            continue;
+          }
+          for (int c = 0; c < en.nchunks; ++c, ++kidx) {
+            if (kidx < kb0 || kidx >= kb1) continue;
             mbar_wait(&empty_bar[stage], phase ^ 1);
             mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
             uint8_t* sa = smem + stage * stage_bytes;
@@ -131,11 +142,13 @@ pcm_gemm_kernel(const __grid_constant__ GemmParams p) {
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const int ks = item % p.ksplit;
+        const int nkb = min(p.num_kblocks, (ks + 1) * kb_per) - ks * kb_per;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256;
-        for (int kb = 0; kb < p.num_kblocks; ++kb) {
+        for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
@@ -176,7 +189,8 @@ pcm_gemm_kernel(const __grid_constant__ GemmParams p) {
     const bool has_rv = p.rowvec != nullptr, has_alpha = p.alpha != 1.0f;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      const int tile = item / p.ksplit;
       const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
       const int n0 = tn * p.block_n;
       long long off[4];
@@ -266,6 +280,13 @@ pcm_gemm_kernel(const __grid_constant__ GemmParams p) {
               for (int e = 0; e < 8; ++e) f[e] *= p.alpha;
             }
             const long long o = off[i];
+            if (p.ws) {  // split-K partial sums (fp32 atomics; finalize kernel applies the epilogue)
+              float* wp = p.ws + static_cast<long long>(tm * 128 + rr) * p.N + n;
+#pragma unroll
+              for (int e = 0; e < 8; ++e)
+                if (n + e < p.N) atomicAdd(wp + e, f[e]);
+              continue;
+            }
             if (full8) {
               if (has_bias) {
                 f[0] += bia0.x; f[1] += bia0.y; f[2] += bia0.z; f[3] += bia0.w;
@@ -337,6 +358,36 @@ pcm_gemm_kernel(const __grid_constant__ GemmParams p) {
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// split-K finalize: out = act(ws + bias + rowvec + residual), same row mapping as the GEMM epilogue
+__global__ void splitk_finalize_kernel(const GemmParams p) {
+  griddep_sync();
+  const int nvec = (p.N + 7) >> 3;
+  const long long total = static_cast<long long>(p.M) * nvec;
+  for (long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; v < total;
+       v += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int m = static_cast<int>(v / nvec);
+    const int n = static_cast<int>(v - static_cast<long long>(m) * nvec) * 8;
+    const int b = m / p.epiHW;
+    const int r = m - b * p.epiHW;
+    const int h = r / p.epiW;
+    const int w = r - h * p.epiW;
+    const long long o = b * p.osB + h * p.osH + w * p.osW;
+    for (int e = 0; e < 8 && n + e < p.N; ++e) {
+      float x = p.ws[static_cast<long long>(m) * p.N + n + e];
+      if (p.bias) x += p.bias[n + e];
+      if (p.rowvec) x += __bfloat162float(p.rowvec[b * p.rowvec_ld + n + e]);
+      if (p.residual) x += __bfloat162float(p.residual[o + n + e]);
+      if (p.act == 1) x = silu_f(x);
+      if (p.out_fp32) {
+        if (p.round_bf16) x = __bfloat162float(__float2bfloat16_rn(x));
+        reinterpret_cast<float*>(p.out)[o + n + e] = x;
+      } else {
+        reinterpret_cast<bf16*>(p.out)[o + n + e] = __float2bfloat16_rn(x);
+      }
+    }
   }
 }
 
@@ -563,6 +614,15 @@ static int launch_gemm(const pcm_gemm_desc* d, cudaStream_t stream) {
   p.round_bf16 = d->round_bf16;
   p.alpha = d->alpha;
   p.act = d->act;
+  p.ksplit = 1;
+  p.ws = nullptr;
+  if (d->ksplit > 1 && d->splitk_ws != nullptr) {
+    int ks = d->ksplit;
+    if (ks > nkb) ks = nkb;
+    const int per = (nkb + ks - 1) / ks;
+    ks = (nkb + per - 1) / per;  // every split non-empty
+    p.ksplit = ks;
+  }
 
   const size_t smem = static_cast<size_t>(S) * stage_bytes + kStagingBytes + 1024;
   static bool attr_set = false;
@@ -571,8 +631,24 @@ static int launch_gemm(const pcm_gemm_desc* d, cudaStream_t stream) {
                                   kSmemLimit));
     attr_set = true;
   }
-  const int tiles = p.tiles_m * p.tiles_n;
+  const int tiles = p.tiles_m * p.tiles_n * p.ksplit;
   const int grid = tiles < num_sms() ? tiles : num_sms();
+  if (p.ksplit > 1) {
+    // pass 1: fp32 partial sums into the workspace; pass 2: epilogue
+    GemmParams q = p;
+    q.ws = reinterpret_cast<float*>(d->splitk_ws);
+    q.bias = nullptr; q.rowvec = nullptr; q.residual = nullptr; q.act = 0;
+    CUDA_TRY(cudaMemsetAsync(q.ws, 0, sizeof(float) * static_cast<size_t>(p.M) * p.N, stream));
+    CUDA_TRY(launch_pdl(pcm_gemm_kernel, dim3(grid), dim3(kGemmThreads), smem, stream, q));
+    GemmParams f = p;
+    f.ws = q.ws;
+    f.alpha = 1.f;
+    const long long nv = static_cast<long long>(p.M) * ((p.N + 7) / 8);
+    int fg = static_cast<int>((nv + 255) / 256);
+    if (fg > num_sms() * 8) fg = num_sms() * 8;
+    CUDA_TRY(launch_pdl(splitk_finalize_kernel, dim3(fg), dim3(256), 0, stream, f));
+    return 0;
+  }
   CUDA_TRY(launch_pdl(pcm_gemm_kernel, dim3(grid), dim3(kGemmThreads), smem, stream, p));
   CUDA_TRY(cudaGetLastError());
   return 0;

@@ -69,9 +69,24 @@ def pick_block_n(M, N):
     return best
 
 
+def pick_tiling(M, N, nkb):
+    """(block_n, ksplit): small-M long-K GEMMs (the 8x8 / 16x16 UNet levels, LoRA-A convs) leave most
+    SMs idle with one CTA per output tile, so their K loop is split over several CTAs."""
+    sms = num_sms()
+    tiles_m = (M + 127) // 128
+    if nkb >= 32:
+        bn = min(256, ((N + 31) // 32) * 32)          # widest tile: best operand reuse
+        tiles = tiles_m * ((N + bn - 1) // bn)
+        if tiles * 2 <= sms:
+            ks = min(nkb // 8, sms // tiles)
+            if ks >= 2:
+                return bn, ks
+    return pick_block_n(M, N), 1
+
+
 def gemm(a_srcs, b_srcs, prog, *, lin, M, N, out, geo=(1, 1), bias=None, rowvec=None,
          residual=None, out_strides=None, epi=None, alpha=1.0, act=0, round_bf16=False,
-         block_n=None):
+         block_n=None, ksplit=None):
     """Launch the tcgen05 implicit GEMM.  prog: list of (a_src, b_src, dw, dh, nchunks, a_c0, b_k0).
 
     out: bf16 or fp32 tensor; rows are addressed as b*osB + h*osH + w*osW with (osW, osH, osB) =
@@ -86,7 +101,15 @@ def gemm(a_srcs, b_srcs, prog, *, lin, M, N, out, geo=(1, 1), bias=None, rowvec=
     d.num_a, d.num_b, d.num_prog = len(a_srcs), len(b_srcs), len(prog)
     d.lin, d.M, d.N = int(lin), M, N
     d.geoW, d.geoH = geo
+    nkb = sum(e[4] for e in prog)
+    if block_n is None and ksplit is None:
+        block_n, ksplit = pick_tiling(M, N, nkb)
     d.block_n = block_n or pick_block_n(M, N)
+    d.ksplit = ksplit or 1
+    ws = None
+    if d.ksplit > 1:
+        ws = torch.empty(M, N, device=out.device, dtype=torch.float32) if DRY_RUN is None else None
+        d.splitk_ws = ws.data_ptr() if ws is not None else 0
     d.out = out.data_ptr()
     d.out_fp32 = int(out.dtype == torch.float32)
     assert out.dtype in (torch.float32, BF16)
@@ -115,7 +138,7 @@ def gemm(a_srcs, b_srcs, prog, *, lin, M, N, out, geo=(1, 1), bias=None, rowvec=
     LAUNCHES["count"] += 1
     if DRY_RUN is not None:
         DRY_RUN.append(("gemm", dict(M=M, N=N, K=64 * sum(e[4] for e in prog), bn=d.block_n, lin=int(lin),
-                                     nprog=len(prog), res=residual is not None)))
+                                     nprog=len(prog), res=residual is not None, ksplit=d.ksplit)))
         return out
     if PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -129,3 +129,24 @@ def test_wgrad_conv_taps(cuda):
     y.backward(dt.float().permute(0, 3, 1, 2))
     ref = a.grad.permute(0, 2, 3, 1).reshape(64, 9, Cin)
     _close(out, ref, tol=2e-3)
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(8, 8, 8, 1280, 1280), (8, 8, 8, 1280, 64), (2, 16, 16, 640, 64)])
+def test_conv3x3_splitk(cuda, B, H, W, Cin, Cout):
+    """Small-M long-K convolutions run split-K (fp32 atomics + finalize kernel)."""
+    from pcm_b200 import ops
+    x = _rand((B, H, W, Cin), cuda, 1)
+    w = _rand((Cout, Cin, 3, 3), cuda, 2, (9 * Cin) ** -0.5)
+    bias = torch.randn(Cout, device=cuda)
+    res = _rand((B, H, W, Cout), cuda, 5)
+    rowvec = _rand((B, Cout), cuda, 4)
+    out = torch.empty(B, H, W, Cout, device=cuda, dtype=torch.bfloat16)
+    prog = [(0, 0, dw, dh, Cin // 64, 0, t * Cin) for t, (dw, dh) in enumerate(ops.TAPS3)]
+    M = B * H * W
+    bn, ks = ops.pick_tiling(M, Cout, len(prog) * (Cin // 64))
+    assert ks > 1
+    ops.gemm([ops.asrc_nhwc(x)], [ops.bsrc(_wmat_conv(w))], prog, lin=False, M=M, N=Cout,
+             geo=(W, H), out=out.view(-1, Cout), bias=bias, rowvec=rowvec, residual=res.view(-1, Cout), act=1)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias, padding=1)
+    ref = F.silu(ref + rowvec.float()[:, :, None, None] + res.float().permute(0, 3, 1, 2))
+    _close(out.permute(0, 3, 1, 2), ref)
