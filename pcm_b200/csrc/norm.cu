@@ -16,6 +16,7 @@ namespace pcm {
 // GroupNorm statistics: stats[b, g] = (sum, sumsq) over HW x (C/G) elements
 // ------------------------------------------------------------------------------------------
 constexpr int kGnMaxC = 2560;
+constexpr int kGnStage = 4096;   // ny * C <= 4096 floats of per-thread partials (see gn_launch_cfg)
 
 __device__ __forceinline__ const bf16* gn_src(const bf16* x1, const bf16* x2, int C1, int C2,
                                               long long pix, int c) {
@@ -26,18 +27,15 @@ __global__ void gn_stats_kernel(const bf16* __restrict__ x1, const bf16* __restr
                                 int C2, int HW, int G, int pix_per_block,
                                 float* __restrict__ stats) {
   griddep_sync();
-  __shared__ float s_sum[kGnMaxC];
-  __shared__ float s_sq[kGnMaxC];
+  // per-thread partials are staged as [ty][channel] (plain stores) and tree-summed: shared-memory
+  // atomics cost ~2 cycles per lane and dominated this kernel
+  __shared__ float s_sum[kGnStage];
+  __shared__ float s_sq[kGnStage];
   const int C = C1 + C2;
   const int b = blockIdx.y;
   const int nvec = C >> 3;
   const int tx = threadIdx.x % nvec, ty = threadIdx.x / nvec;
   const int ny = blockDim.x / nvec;
-  for (int i = threadIdx.x; i < C; i += blockDim.x) {
-    s_sum[i] = 0.f;
-    s_sq[i] = 0.f;
-  }
-  __syncthreads();
   const int p0 = blockIdx.x * pix_per_block;
   const int p1 = min(HW, p0 + pix_per_block);
   float a[8], q[8];
@@ -67,11 +65,20 @@ __global__ void gn_stats_kernel(const bf16* __restrict__ x1, const bf16* __restr
         }
       }
     }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      atomicAdd(&s_sum[c + i], a[i]);
-      atomicAdd(&s_sq[c + i], q[i]);
+    *reinterpret_cast<float4*>(&s_sum[ty * C + c]) = make_float4(a[0], a[1], a[2], a[3]);
+    *reinterpret_cast<float4*>(&s_sum[ty * C + c + 4]) = make_float4(a[4], a[5], a[6], a[7]);
+    *reinterpret_cast<float4*>(&s_sq[ty * C + c]) = make_float4(q[0], q[1], q[2], q[3]);
+    *reinterpret_cast<float4*>(&s_sq[ty * C + c + 4]) = make_float4(q[4], q[5], q[6], q[7]);
+  }
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
+    float s = 0.f, ss = 0.f;
+    for (int y = 0; y < ny; ++y) {
+      s += s_sum[y * C + ch];
+      ss += s_sq[y * C + ch];
     }
+    s_sum[ch] = s;   // row 0 now holds the block totals (each thread only touches its own column)
+    s_sq[ch] = ss;
   }
   __syncthreads();
   const int cpg = C / G;
@@ -157,8 +164,8 @@ __global__ void gn_bwd_stats_kernel(const bf16* __restrict__ dy, const bf16* __r
                                     const float* __restrict__ gamma, const float* __restrict__ beta,
                                     float eps, int silu, float* __restrict__ red) {
   griddep_sync();
-  __shared__ float s_a[kGnMaxC];
-  __shared__ float s_b[kGnMaxC];
+  __shared__ float s_a[kGnStage];
+  __shared__ float s_b[kGnStage];
   const int C = C1 + C2;
   const int b = blockIdx.y;
   const int nvec = C >> 3;
@@ -166,11 +173,6 @@ __global__ void gn_bwd_stats_kernel(const bf16* __restrict__ dy, const bf16* __r
   const int ny = blockDim.x / nvec;
   const int cpg = C / G;
   const float inv_n = 1.f / (static_cast<float>(HW) * cpg);
-  for (int i = threadIdx.x; i < C; i += blockDim.x) {
-    s_a[i] = 0.f;
-    s_b[i] = 0.f;
-  }
-  __syncthreads();
   const int p0 = blockIdx.x * pix_per_block;
   const int p1 = min(HW, p0 + pix_per_block);
   if (ty < ny) {
@@ -209,11 +211,20 @@ __global__ void gn_bwd_stats_kernel(const bf16* __restrict__ dy, const bf16* __r
         }
       }
     }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      atomicAdd(&s_a[c + i], a[i]);
-      atomicAdd(&s_b[c + i], q[i]);
+    *reinterpret_cast<float4*>(&s_a[ty * C + c]) = make_float4(a[0], a[1], a[2], a[3]);
+    *reinterpret_cast<float4*>(&s_a[ty * C + c + 4]) = make_float4(a[4], a[5], a[6], a[7]);
+    *reinterpret_cast<float4*>(&s_b[ty * C + c]) = make_float4(q[0], q[1], q[2], q[3]);
+    *reinterpret_cast<float4*>(&s_b[ty * C + c + 4]) = make_float4(q[4], q[5], q[6], q[7]);
+  }
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
+    float s = 0.f, ss = 0.f;
+    for (int y = 0; y < ny; ++y) {
+      s += s_a[y * C + ch];
+      ss += s_b[y * C + ch];
     }
+    s_a[ch] = s;
+    s_b[ch] = ss;
   }
   __syncthreads();
   for (int g = threadIdx.x; g < G; g += blockDim.x) {
@@ -480,7 +491,7 @@ static inline int ln_lpr(int C) {
 static int gn_launch_cfg(int C, int HW, int B, int* threads, int* ppb, int* nblk) {
   const int nvec = C / 8;
   if (C % 8 != 0 || C > kGnMaxC || nvec > 1024) return set_error("groupnorm: unsupported C");
-  int ny = 512 / nvec;
+  int ny = 512 / nvec;      // ny * nvec <= 512 threads  =>  ny * C <= 4096 staged floats
   if (ny < 1) ny = 1;
   *threads = nvec * ny;
   // ~4 waves of blocks over the chip

@@ -79,6 +79,7 @@ class PCMTrainStep:
         self.noisy = self.noisy2[:B]
         self.start_t2 = torch.zeros(2 * B, **i64)
         self.graph = None
+        self.graph_opt = None
 
     def set_lr(self, lr):
         self.opt_state[0] = lr
@@ -115,10 +116,14 @@ class PCMTrainStep:
         u.backward(self.d_eps)
 
     def optimizer_step(self):
+        if self.world > 1:
+            # ONE collective per step: SUM of the flat LoRA gradient; 1/world is folded into AdamW
+            torch.distributed.all_reduce(self.unet.lora_grad, group=self.pg)
+        self._optimizer_kernels()
+
+    def _optimizer_kernels(self):
         u = self.unet
         g = u.lora_grad
-        if self.world > 1:
-            torch.distributed.all_reduce(g, group=self.pg)  # sum; the 1/world is folded into AdamW
         ops._call("pcm_grad_sumsq", g.data_ptr(), g.numel(), self.sumsq.data_ptr())
         ops._call("pcm_adamw_clip", u.lora_master.data_ptr(), g.data_ptr(), self.exp_avg.data_ptr(),
                   self.exp_avg_sq.data_ptr(), g.numel(), self.opt_state.data_ptr(), self.betas[0],
@@ -133,7 +138,10 @@ class PCMTrainStep:
         return self.loss
 
     def capture(self, warmup=2):
-        """Capture forward+backward+optimiser into one CUDA graph (after eager warm-up runs)."""
+        """Capture the iteration into CUDA graph(s) after eager warm-up runs.  Single GPU: one graph
+        for forward + backward + optimiser.  Data parallel: the NCCL all-reduce is captured inside
+        the same graph when the installed NCCL supports it, otherwise the step is split into
+        graph(forward+backward) -> eager all-reduce -> graph(optimiser)."""
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         snap = (self.unet.lora_master.clone(), self.exp_avg.clone(), self.exp_avg_sq.clone(),
@@ -142,10 +150,25 @@ class PCMTrainStep:
             for _ in range(warmup):
                 self.run_eager()
         torch.cuda.current_stream().wait_stream(s)
-        self.graph = torch.cuda.CUDAGraph()
+        torch.cuda.synchronize()
+        self.graph, self.graph_opt = None, None
         n0 = ops.LAUNCHES["count"]
-        with torch.cuda.graph(self.graph):
-            self.run_eager()
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.run_eager()
+            self.graph = g
+        except Exception:
+            if self.world == 1:
+                raise
+            torch.cuda.synchronize()
+            n0 = ops.LAUNCHES["count"]
+            g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g1):
+                self.forward_backward()
+            with torch.cuda.graph(g2):
+                self._optimizer_kernels()
+            self.graph, self.graph_opt = g1, g2
         ops.LAUNCHES["per_step"] = ops.LAUNCHES["count"] - n0
         # the warm-up / capture runs must not count as training steps
         self.unet.lora_master.copy_(snap[0])
@@ -166,8 +189,12 @@ class PCMTrainStep:
         self.in_uncond.copy_(uncond.reshape(self.in_uncond.shape), non_blocking=non_blocking)
 
     def step(self):
-        if self.graph is not None:
+        if self.graph is None:
+            self.run_eager()
+        elif getattr(self, "graph_opt", None) is None:
             self.graph.replay()
         else:
-            self.run_eager()
+            self.graph.replay()
+            torch.distributed.all_reduce(self.unet.lora_grad, group=self.pg)
+            self.graph_opt.replay()
         return self.loss

@@ -110,6 +110,42 @@ class UNetB200:
             self.refresh_work = work
             self.refresh_lora()
         self.saved = None
+        # LoRA weight-gradient GEMMs are off the dgrad critical path (they only feed the optimiser):
+        # they run on a side stream and fill SMs the main backward chain leaves idle
+        import os as _os
+        self.use_wstream = (torch.device(device).type == "cuda" and need_backward and lora and
+                            _os.environ.get("PCM_WGRAD_STREAM", "1") != "0")
+        self.wstream = torch.cuda.Stream(device=device) if self.use_wstream else None
+        self._keep = []
+
+    class _Side:
+        """Run the enclosed launches on the wgrad side stream, ordered after everything enqueued so far
+        on the current stream; `keep` tensors stay referenced until backward() joins the streams."""
+
+        def __init__(self, net, keep):
+            self.net, self.keep, self.ctx = net, keep, None
+
+        def __enter__(self):
+            n = self.net
+            if not n.use_wstream:
+                return self
+            ev = torch.cuda.Event()
+            ev.record()
+            n.wstream.wait_event(ev)
+            n._keep.extend(self.keep)
+            self.ctx = torch.cuda.stream(n.wstream)
+            self.ctx.__enter__()
+            return self
+
+        def __exit__(self, *a):
+            if self.ctx is not None:
+                self.ctx.__exit__(*a)
+            return False
+
+    def _join_side(self):
+        if self.use_wstream:
+            torch.cuda.current_stream().wait_stream(self.wstream)
+            self._keep.clear()
 
     # ------------------------------------------------------------------------------------
     def refresh_lora(self):
@@ -366,12 +402,13 @@ class UNetB200:
     def _lora_wgrads(self, L, P_list, dy_mat, T_mat, dt_mat, taps_desc, lin, geo, M):
         """dB += s * dy^T T ;  dA += dt^T x  (per source / tap group)."""
         lo = L.lora
-        ops.wgrad(ops.asrc_mat(dy_mat), ops.asrc_mat(T_mat), lo.gB, lin=True, M=M, os_row=self.r, os_col=1,
-                  alpha=self.scale)
-        ktot = lo.gA.shape[1]
-        for (psrc, taps, offs) in P_list:
-            ops.wgrad(psrc, taps_desc(dt_mat), lo.gA, lin=lin, M=M, geo=geo, taps=taps, tap_off=offs,
-                      os_row=1, os_col=ktot)
+        with UNetB200._Side(self, (dy_mat, T_mat, dt_mat, P_list)):
+            ops.wgrad(ops.asrc_mat(dy_mat), ops.asrc_mat(T_mat), lo.gB, lin=True, M=M, os_row=self.r, os_col=1,
+                      alpha=self.scale)
+            ktot = lo.gA.shape[1]
+            for (psrc, taps, offs) in P_list:
+                ops.wgrad(psrc, taps_desc(dt_mat), lo.gA, lin=lin, M=M, geo=geo, taps=taps, tap_off=offs,
+                          os_row=1, os_col=ktot)
 
     def linear_bwd(self, rec, dy, need_dx=True, accumulate=None):
         """rec = ("linear", name, xs, T).  Returns dx [M, cin_total] (or None)."""
@@ -388,6 +425,7 @@ class UNetB200:
             for x in xs:
                 P_list.append((ops.asrc_mat(x), ((0, 0),), (coff,)))
                 coff += x.shape[1]
+            self._keep.extend(xs)
             self._lora_wgrads(L, P_list, dy, T, dt, ops.asrc_mat, True, (1, 1), M)
         if not need_dx:
             return None
@@ -432,12 +470,13 @@ class UNetB200:
                                     offs.append((kh * 3 + kw) * L.cin)
                         P_list.append((ops.asrc_nhwc(x[:, p::2, q::2, :]), taps, offs))
             lo = L.lora
-            ops.wgrad(ops.asrc_mat(dy_m), ops.asrc_mat(T.view(M, self.r)), lo.gB, lin=True, M=M,
-                      os_row=self.r, os_col=1, alpha=self.scale)
-            ktot = lo.gA.shape[1]
-            for (psrc, taps, offs) in P_list:
-                ops.wgrad(psrc, ops.asrc_nhwc(dt), lo.gA, lin=False, M=M, geo=geo, taps=taps, tap_off=offs,
-                          os_row=1, os_col=ktot)
+            with UNetB200._Side(self, (dy, T, dt, xs)):
+                ops.wgrad(ops.asrc_mat(dy_m), ops.asrc_mat(T.view(M, self.r)), lo.gB, lin=True, M=M,
+                          os_row=self.r, os_col=1, alpha=self.scale)
+                ktot = lo.gA.shape[1]
+                for (psrc, taps, offs) in P_list:
+                    ops.wgrad(psrc, ops.asrc_nhwc(dt), lo.gA, lin=False, M=M, geo=geo, taps=taps, tap_off=offs,
+                              os_row=1, os_col=ktot)
         if not need_dx:
             return None
         cin = L.cin
@@ -627,4 +666,5 @@ class UNetB200:
                 r = self.resnet_bwd(recs, d, need_dx=not first)
                 if not first:
                     d = r[0].view(Bc, Hc, Wc, -1)
+        self._join_side()
         self.saved = None
