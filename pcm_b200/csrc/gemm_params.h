@@ -1,0 +1,36 @@
+// Kernel parameter block shared by the 1-CTA and 2-CTA tcgen05 implicit-GEMM kernels.
+#pragma once
+#include <cuda.h>
+#include "common.cuh"
+#include "../../include/pcm_b200.h"
+
+namespace pcm {
+
+struct KEntry {
+  int a_map, b_map, dw, dh, nchunks, a_c0, b_k0, pad_;
+};
+
+struct alignas(64) GemmParams {
+  CUtensorMap a_maps[PCM_MAX_ASRC];
+  CUtensorMap b_maps[PCM_MAX_BSRC];
+  KEntry prog[PCM_MAX_PROG];
+  int num_prog, lin;
+  int M, N;
+  int geoW, geoHW;
+  int block_n, tiles_m, tiles_n, num_kblocks, num_stages;
+  void* out;
+  const float* bias;
+  const bf16* rowvec;
+  const bf16* residual;
+  long long osW, osH, osB, rowvec_ld;
+  int epiW, epiHW;
+  int out_fp32, round_bf16;
+  float alpha;
+  int act;
+  int ksplit;        // > 1: work item = (tile, K split); fp32 partial sums are atomically added
+  float* ws;         // into ws[m * N + n]; bias / residual / activation run in the finalize kernel
+};
+
+constexpr int kATileBytes = 128 * 128;  // 128 rows x 64 bf16
+
+}  // namespace pcm

@@ -16,38 +16,16 @@
 #include "common.cuh"
 #include "host_common.h"
 #include "../../include/pcm_b200.h"
+#include "gemm_params.h"
+#include "gemm_epilogue.cuh"
 
 namespace pcm {
 
-struct KEntry {
-  int a_map, b_map, dw, dh, nchunks, a_c0, b_k0, pad_;
-};
-
-struct alignas(64) GemmParams {
-  CUtensorMap a_maps[PCM_MAX_ASRC];
-  CUtensorMap b_maps[PCM_MAX_BSRC];
-  KEntry prog[PCM_MAX_PROG];
-  int num_prog, lin;
-  int M, N;
-  int geoW, geoHW;
-  int block_n, tiles_m, tiles_n, num_kblocks, num_stages;
-  void* out;
-  const float* bias;
-  const bf16* rowvec;
-  const bf16* residual;
-  long long osW, osH, osB, rowvec_ld;
-  int epiW, epiHW;
-  int out_fp32, round_bf16;
-  float alpha;
-  int act;
-  int ksplit;        // > 1: work item = (tile, K split); fp32 partial sums are atomically added
-  float* ws;         // into ws[m * N + n]; bias / residual / activation run in the finalize kernel
-};
+int launch_gemm2(GemmParams& p, const pcm_gemm_desc* d, cudaStream_t stream);  // gemm2_tc.cu
 
 constexpr int kGemmThreads = 320;   // warp0 TMA, warp1 MMA, warps 2-9 epilogue (two groups of 4)
 constexpr int kWgradThreads = 192;
 constexpr int kMaxStages = 8;
-constexpr int kATileBytes = 128 * 128;  // 128 rows x 64 bf16
 constexpr int kStagingBytes = 2 * 128 * 32 * 4;  // epilogue transposition buffers (fp32)
 constexpr int kSmemLimit = 227 * 1024 - 512;     // dynamic smem budget (227 KB max minus static)
 
@@ -185,169 +163,16 @@ pcm_gemm_kernel(const __grid_constant__ GemmParams p) {
     const int cg = et & 3;                    // 8-column group inside the 32-column chunk
     const int r0 = et >> 2;                   // phase-2 rows: r0 + 32 * i
     float* sb = reinterpret_cast<float*>(smem + S * stage_bytes) + grp * (128 * 32);
-    const bool has_bias = p.bias != nullptr, has_res = p.residual != nullptr;
-    const bool has_rv = p.rowvec != nullptr, has_alpha = p.alpha != 1.0f;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
       const int tile = item / p.ksplit;
       const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
       const int n0 = tn * p.block_n;
-      long long off[4];
-      const bf16* rvp[4];
-      bool valid[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int m = tm * 128 + r0 + 32 * i;
-        valid[i] = m < p.M;
-        off[i] = 0;
-        rvp[i] = nullptr;
-        if (valid[i]) {
-          const int b = m / p.epiHW;
-          const int r = m - b * p.epiHW;
-          const int h = r / p.epiW;
-          const int w = r - h * p.epiW;
-          off[i] = b * p.osB + h * p.osH + w * p.osW;
-          if (has_rv) rvp[i] = p.rowvec + b * p.rowvec_ld;
-        }
-      }
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256;
-      const int nchunks = p.block_n >> 5;
-      const int last_j = ((nchunks - 1 - grp) & ~1) + grp;  // last chunk this group handles
-      if (grp >= nchunks) {  // block_n == 32: group 1 has no chunk, still releases the accumulator
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-      }
-      for (int j = grp; j < nchunks; j += 2) {
-        const int n = n0 + j * 32 + cg * 8;
-        const bool full8 = n + 8 <= p.N;
-        // Issue every global read of this chunk's phase 2 up front (bias, row vectors, residual):
-        // their latency overlaps the TMEM load / staging / barrier, and nothing is re-read after a
-        // store (out may alias residual for in-place accumulation, each element by the same thread).
-        float4 bia0 = make_float4(0.f, 0.f, 0.f, 0.f), bia1 = bia0;
-        uint4 rres[4], rrv[4];
-        if (full8) {
-          if (has_bias) {
-            bia0 = *reinterpret_cast<const float4*>(p.bias + n);
-            bia1 = *reinterpret_cast<const float4*>(p.bias + n + 4);
-          }
-          if (has_res) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              if (valid[i]) rres[i] = *reinterpret_cast<const uint4*>(p.residual + off[i] + n);
-          }
-          if (has_rv) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              if (valid[i]) rrv[i] = *reinterpret_cast<const uint4*>(rvp[i] + n);
-          }
-        }
-        {
-          uint32_t v[32];
-          tmem_ld_32x32(taddr + j * 32, v);
-          tmem_ld_wait();
-          if (j == last_j) {
-            // all TMEM reads of this group for this tile are done: release the accumulator
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-          }
-          float* srow = sb + row * 32;
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const int cs = c ^ (row & 7);
-            *reinterpret_cast<float4*>(srow + cs * 4) =
-                make_float4(__uint_as_float(v[4 * c]), __uint_as_float(v[4 * c + 1]),
-                            __uint_as_float(v[4 * c + 2]), __uint_as_float(v[4 * c + 3]));
-          }
-        }
-        // group-local barrier (ids 1 / 2): staging tile written
-        asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");
-        if (n < p.N) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            if (!valid[i]) continue;
-            const int rr = r0 + 32 * i;
-            const float* srow = sb + rr * 32;
-            const float4 a0 = *reinterpret_cast<const float4*>(srow + ((2 * cg) ^ (rr & 7)) * 4);
-            const float4 a1 = *reinterpret_cast<const float4*>(srow + ((2 * cg + 1) ^ (rr & 7)) * 4);
-            float f[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-            if (has_alpha) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) f[e] *= p.alpha;
-            }
-            const long long o = off[i];
-            if (p.ws) {  // split-K partial sums (fp32 atomics; finalize kernel applies the epilogue)
-              float* wp = p.ws + static_cast<long long>(tm * 128 + rr) * p.N + n;
-#pragma unroll
-              for (int e = 0; e < 8; ++e)
-                if (n + e < p.N) atomicAdd(wp + e, f[e]);
-              continue;
-            }
-            if (full8) {
-              if (has_bias) {
-                f[0] += bia0.x; f[1] += bia0.y; f[2] += bia0.z; f[3] += bia0.w;
-                f[4] += bia1.x; f[5] += bia1.y; f[6] += bia1.z; f[7] += bia1.w;
-              }
-              if (has_rv) {
-                float2 t;
-                t = unpack_bf16x2(rrv[i].x); f[0] += t.x; f[1] += t.y;
-                t = unpack_bf16x2(rrv[i].y); f[2] += t.x; f[3] += t.y;
-                t = unpack_bf16x2(rrv[i].z); f[4] += t.x; f[5] += t.y;
-                t = unpack_bf16x2(rrv[i].w); f[6] += t.x; f[7] += t.y;
-              }
-              if (has_res) {
-                float2 t;
-                t = unpack_bf16x2(rres[i].x); f[0] += t.x; f[1] += t.y;
-                t = unpack_bf16x2(rres[i].y); f[2] += t.x; f[3] += t.y;
-                t = unpack_bf16x2(rres[i].z); f[4] += t.x; f[5] += t.y;
-                t = unpack_bf16x2(rres[i].w); f[6] += t.x; f[7] += t.y;
-              }
-              if (p.act == 1) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) f[e] = silu_f(f[e]);
-              }
-              if (p.out_fp32) {
-                if (p.round_bf16) {
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) f[e] = __bfloat162float(__float2bfloat16_rn(f[e]));
-                }
-                float* op = reinterpret_cast<float*>(p.out) + o + n;
-                *reinterpret_cast<float4*>(op) = make_float4(f[0], f[1], f[2], f[3]);
-                *reinterpret_cast<float4*>(op + 4) = make_float4(f[4], f[5], f[6], f[7]);
-              } else {
-                uint4 u;
-                u.x = pack_bf16x2(f[0], f[1]);
-                u.y = pack_bf16x2(f[2], f[3]);
-                u.z = pack_bf16x2(f[4], f[5]);
-                u.w = pack_bf16x2(f[6], f[7]);
-                *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + o + n) = u;
-              }
-            } else {
-              // ragged N tail (e.g. conv_out, N = 4): scalar path
-              const bf16* rv = rvp[i];
-              for (int e = 0; e < 8 && n + e < p.N; ++e) {
-                float x = f[e];
-                if (has_bias) x += p.bias[n + e];
-                if (rv) x += __bfloat162float(rv[n + e]);
-                if (has_res) x += __bfloat162float(p.residual[o + n + e]);
-                if (p.act == 1) x = silu_f(x);
-                if (p.out_fp32) {
-                  if (p.round_bf16) x = __bfloat162float(__float2bfloat16_rn(x));
-                  reinterpret_cast<float*>(p.out)[o + n + e] = x;
-                } else {
-                  reinterpret_cast<bf16*>(p.out)[o + n + e] = __float2bfloat16_rn(x);
-                }
-              }
-            }
-          }
-        }
-        // staging tile consumed: the group may overwrite it in its next chunk
-        asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");
-      }
+      uint64_t* tempty = &tempty_bar[acc];
+      gemm_epilogue_tile(p, tm, n0, taddr, sb, lane, row, grp, cg, r0, &tfull_bar[acc], acc_phase,
+                         [tempty]() { mbar_arrive(tempty); });
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -648,6 +473,10 @@ static int launch_gemm(const pcm_gemm_desc* d, cudaStream_t stream) {
     if (fg > num_sms() * 8) fg = num_sms() * 8;
     CUDA_TRY(launch_pdl(splitk_finalize_kernel, dim3(fg), dim3(256), 0, stream, f));
     return 0;
+  }
+  {
+    const int rc2 = launch_gemm2(p, d, stream);  // 2-CTA kernel for the large layers
+    if (rc2 <= 0) return rc2;
   }
   CUDA_TRY(launch_pdl(pcm_gemm_kernel, dim3(grid), dim3(kGemmThreads), smem, stream, p));
   CUDA_TRY(cudaGetLastError());
