@@ -101,51 +101,64 @@ def synth_batch(cfg, B, hw, seed, pinned=True):
     return t
 
 
-def cpu_reference_sample(threads=None, repeats=1, hw=64, multiphase=4):
-    """Times the restated reference loop (oracle) on the host cores on a bounded sample: ONE sample
-    (1/8 of a per-GPU batch) of the bs-8 512x512 workload, fp32, forward x4 + backward.
-    Returns (seconds per sample-step, cores)."""
+# algorithmic FLOPs of ONE LoRA-student forward of one sample (F + L), by latent size
+FWD_FLOP = {64: 803.6e9 + 94.3e9, 32: 180.2e9 + 24.0e9}
+STEP_FLOP = {64: FLOP_PER_SAMPLE_64, 32: 1.006e12}
+
+
+def cpu_forward_sample(hw=64, repeats=1, threads=None):
+    """Bounded CPU sample of the workload: ONE LoRA-student UNet forward of ONE sample through the
+    restated reference (oracle, fp32, all host threads).  Returns (seconds, cores)."""
     from oracle import pcm_ref, unet_ref
     cores = threads or os.cpu_count() or 1
     torch.set_num_threads(cores)
     cfg = unet_ref.SD15
     P = unet_ref.init_params(cfg, 0)
     batch = pcm_ref.make_batch(cfg, 1, hw, seed=0)
-    times = []
-    for _ in range(repeats):
-        t0 = time.perf_counter()
-        pcm_ref.pcm_step_ref(cfg, P, batch, multiphase=multiphase, emulate_bf16=False, need_grad=True)
-        times.append(time.perf_counter() - t0)
-    return min(times), cores
+    net = unet_ref.UNetRef(cfg, P, use_lora=True)
+    ts = torch.tensor([499])
+    best = None
+    with torch.no_grad():
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            net(batch["latents"], ts, batch["prompt_embeds"])
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+    return best, cores
+
+
+def cpu_steps_per_s(t_fwd, hw, batch=8):
+    """Scale the forward sample to the metric: a bs-`batch` step costs STEP_FLOP / FWD_FLOP forwards
+    per sample (5F + A + 4L vs F + L) at 64x64 latents."""
+    t_step_sample_64 = t_fwd * (FWD_FLOP[64] / FWD_FLOP[hw]) * (STEP_FLOP[64] / FWD_FLOP[64])
+    return 1.0 / (batch * t_step_sample_64)
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU path (oracle port; diffusers/peft/accelerate are not
-    installable offline so the unmodified reference cannot run).  Rank 0 only."""
+    """--impl reference: the reference's CPU path.  diffusers / peft / accelerate cannot be installed
+    offline, so the unmodified reference cannot run; this arm times the oracle port (the reference
+    loop restated in plain PyTorch) on the host cores.  Rank 0 only."""
     if rank != 0:
         return
+    hw = 64 if (args.steps + args.warmup) <= 5 else 32
     per = []
-    from oracle import pcm_ref, unet_ref
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    cfg = unet_ref.SD15
-    P = unet_ref.init_params(cfg, 0)
-    batch = pcm_ref.make_batch(cfg, 1, 64, seed=0)
     for i in range(args.warmup + args.steps):
-        t0 = time.perf_counter()
-        pcm_ref.pcm_step_ref(cfg, P, batch, multiphase=4, emulate_bf16=False, need_grad=True)
-        dt = time.perf_counter() - t0
+        t, cores = cpu_forward_sample(hw)
         if i >= args.warmup:
-            per.append(dt)
-    t_sample = sum(per) / len(per)
-    value = 1.0 / (8.0 * t_sample)  # a bs-8 step = 8 such samples
-    sample = "1 of the 8 samples of a bs-8 512x512 step (fp32, 4 UNet forwards + backward, torch CPU); value = 1/(8*t)"
+            per.append(t)
+    t_fwd = sum(per) / len(per)
+    value = cpu_steps_per_s(t_fwd, hw)
+    sample = (f"each step = one fp32 LoRA-student UNet forward of ONE {hw}x{hw}-latent sample through the "
+              f"restated reference (torch CPU, {cores} threads, {t_fwd:.2f} s); scaled to a bs-8 64x64 step by "
+              "the algorithmic FLOP ratio (5F+A+4L)/(F+L) x 8 samples")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 8.0 * t_sample * 1e3,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / value,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "SD1.5 PCM-LoRA 4-phase, bs=8/GPU, 512x512 (64x64 latents), CFG solver on",
-                   "note": "reference loop restated on CPU (oracle port); one bounded sample per step"},
+        "config": {"workload": "SD1.5 PCM-LoRA 4-phase, bs=8/GPU, 512x512 (64x64x4 latents), LoRA r=64, "
+                               "CFG solver on, Huber, AdamW",
+                   "note": "reference loop restated on CPU (oracle port); bounded sample per step"},
         "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -281,10 +294,11 @@ def main():
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline and world == 1:
-            t_s, cores = cpu_reference_sample()
-            cpu = {"value": 1.0 / (8.0 * t_s), "unit": "steps/s", "cores": cores, "kind": "port",
-                   "sample": "1 of the 8 samples of one bs-8 512x512 step through the restated reference loop "
-                             f"(oracle, fp32, torch CPU, {cores} threads): {t_s:.2f} s; value = 1/(8*t)"}
+            t_f, cores = cpu_forward_sample(64)
+            cpu = {"value": cpu_steps_per_s(t_f, 64), "unit": "steps/s", "cores": cores, "kind": "port",
+                   "sample": "one fp32 LoRA-student UNet forward of ONE 64x64-latent sample through the restated "
+                             f"reference (oracle, torch CPU, {cores} threads): {t_f:.2f} s; scaled to a bs-8 step by "
+                             "the algorithmic FLOP ratio (5F+A+4L)/(F+L) x 8 samples"}
         line = {
             "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
