@@ -122,18 +122,20 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ x1, const bf16* __restr
   }
   const int p0 = blockIdx.x * pix_per_block;
   const int p1 = min(HW, p0 + pix_per_block);
-  for (int p = p0 + ty; p < p1; p += 2 * ny) {
-    const long long pixa = static_cast<long long>(b) * HW + p;
-    const bool two = p + ny < p1;
-    const long long pixb = pixa + ny;
-    const uint4 ua = *reinterpret_cast<const uint4*>(gn_src(x1, x2, C1, C2, pixa, c));
-    uint4 ub = make_uint4(0, 0, 0, 0);
-    if (two) ub = *reinterpret_cast<const uint4*>(gn_src(x1, x2, C1, C2, pixb, c));
+  constexpr int U = 4;  // independent 16-byte loads in flight per thread
+  for (int p = p0 + ty; p < p1; p += U * ny) {
+    uint4 u[U];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      if (h == 1 && !two) break;
-      const uint4 u = h == 0 ? ua : ub;
-      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    for (int k = 0; k < U; ++k) {
+      const int pp = p + k * ny;
+      if (pp < p1)
+        u[k] = *reinterpret_cast<const uint4*>(gn_src(x1, x2, C1, C2, static_cast<long long>(b) * HW + pp, c));
+    }
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const int pp = p + k * ny;
+      if (pp >= p1) break;
+      const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
       float f[8];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -152,7 +154,7 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ x1, const bf16* __restr
       o.y = pack_bf16x2(f[2], f[3]);
       o.z = pack_bf16x2(f[4], f[5]);
       o.w = pack_bf16x2(f[6], f[7]);
-      *reinterpret_cast<uint4*>(out + (h == 0 ? pixa : pixb) * C + c) = o;
+      *reinterpret_cast<uint4*>(out + (static_cast<long long>(b) * HW + pp) * C + c) = o;
     }
   }
 }

@@ -4,6 +4,8 @@ step, target forward, Huber loss, backward, gradient all-reduce, clip + AdamW) a
 of C-ABI kernel launches, capturable in ONE CUDA graph (no host sync inside; `index`, `w`,
 timesteps, lr and the optimiser step counter live in device memory).
 """
+import os
+
 import numpy as np
 import torch
 
@@ -72,12 +74,15 @@ class PCMTrainStep:
         self.in_w = torch.zeros(B, **f32)
         # prompt and uncond embeddings are the two halves of ONE buffer so that the two teacher
         # passes of the CFG solve (T15:1219-1244) run as a single batch-2B forward
-        self.in_ctx2 = torch.zeros(2 * B * 77, cfg.cross_attention_dim, device=device, dtype=BF16)
-        self.in_prompt = self.in_ctx2[:B * 77]
-        self.in_uncond = self.in_ctx2[B * 77:]
-        self.noisy2 = torch.zeros(2 * B, height, width, 4, **f32)
-        self.noisy = self.noisy2[:B]
-        self.start_t2 = torch.zeros(2 * B, **i64)
+        # student + teacher(cond) + teacher(uncond) run as ONE batch-3B pass (LoRA on the first B
+        # samples only): ctx3 = [prompt; prompt; uncond], noisy3 = 3 x noisy
+        self.in_ctx3 = torch.zeros(3 * B * 77, cfg.cross_attention_dim, device=device, dtype=BF16)
+        self.in_prompt = self.in_ctx3[:B * 77]
+        self.in_uncond = self.in_ctx3[2 * B * 77:]
+        self.noisy3 = torch.zeros(3 * B, height, width, 4, **f32)
+        self.noisy = self.noisy3[:B]
+        self.start_t3 = torch.zeros(3 * B, **i64)
+        self.merged = os.environ.get("PCM_MERGE_PASSES", "1") != "0"
         self.graph = None
         self.graph_opt = None
 
@@ -93,18 +98,28 @@ class PCMTrainStep:
                   self.coef.data_ptr(), self.start_t.data_ptr(), self.t.data_ptr(), self.end_t.data_ptr())
         ops._call("pcm_add_noise", self.in_latents.data_ptr(), self.in_noise.data_ptr(), self.coef.data_ptr(),
                   per, B, self.bf16_mode, self.noisy.data_ptr())
-        eps_s = u.forward(self.noisy, self.start_t, self.in_prompt, lora=True, save=True)
-        if self.apply_cfg:
-            # cond + uncond teacher passes batched: same frozen weights, 2B samples
+        nb = 3 if self.apply_cfg else 2
+        for i in range(1, nb):   # replicate the noisy latents for the teacher samples
             ops._call("pcm_add_noise", self.in_latents.data_ptr(), self.in_noise.data_ptr(),
-                      self.coef.data_ptr(), per, B, self.bf16_mode, self.noisy2[B:].data_ptr())
-            self.start_t2[:B].copy_(self.start_t)
-            self.start_t2[B:].copy_(self.start_t)
-            eps_cu = u.forward(self.noisy2, self.start_t2, self.in_ctx2, lora=False)
-            eps_c, eps_u = eps_cu[:B], eps_cu[B:]
+                      self.coef.data_ptr(), per, B, self.bf16_mode, self.noisy3[i * B:(i + 1) * B].data_ptr())
+            self.start_t3[i * B:(i + 1) * B].copy_(self.start_t)
+        self.start_t3[:B].copy_(self.start_t)
+        self.in_ctx3[B * 77:2 * B * 77].copy_(self.in_prompt)
+        if self.merged:
+            # one pass: [student | teacher cond | teacher uncond]; LoRA only on the student samples
+            eps_all = u.forward(self.noisy3[:nb * B], self.start_t3[:nb * B],
+                                self.in_ctx3 if nb == 3 else self.in_ctx3[:2 * B * 77],
+                                lora=True, save=True, lora_batch=B)
+            eps_s, eps_c = eps_all[:B], eps_all[B:2 * B]
+            eps_u = eps_all[2 * B:] if nb == 3 else eps_c
         else:
-            eps_c = u.forward(self.noisy, self.start_t, self.in_prompt, lora=False)
-            eps_u = eps_c
+            eps_s = u.forward(self.noisy, self.start_t, self.in_prompt, lora=True, save=True)
+            if self.apply_cfg:
+                eps_cu = u.forward(self.noisy3[B:], self.start_t3[B:], self.in_ctx3[B * 77:], lora=False)
+                eps_c, eps_u = eps_cu[:B], eps_cu[B:]
+            else:
+                eps_c = u.forward(self.noisy, self.start_t, self.in_prompt, lora=False)
+                eps_u = eps_c
         ops._call("pcm_teacher_step", eps_c.data_ptr(), eps_u.data_ptr(), self.noisy.data_ptr(),
                   self.coef.data_ptr(), per, B, self.x_prev.data_ptr())
         eps_t = u.forward(self.x_prev, self.t, self.in_prompt, lora=True)

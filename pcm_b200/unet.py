@@ -110,6 +110,7 @@ class UNetB200:
             self.refresh_work = work
             self.refresh_lora()
         self.saved = None
+        self._lb = (1, 1)
         # LoRA weight-gradient GEMMs are off the dgrad critical path (they only feed the optimiser):
         # they run on a side stream and fill SMs the main backward chain leaves idle
         import os as _os
@@ -219,10 +220,14 @@ class UNetB200:
         srcs, prog = self._conv_prog(xs, 3, stride, L.cin)
         bs = [ops.bsrc(L.w_fwd)]
         T = None
+        lbn = self._lrows(B)   # samples that carry the LoRA adapter (the leading ones of the batch)
         if lora and L.lora is not None:
-            T = self._new(B, Ho, Wo, self.r)
-            ops.gemm(srcs, [ops.bsrc(L.lora.a_fwd)], prog, lin=False, M=M, N=self.r, geo=(Wo, Ho),
-                     out=T.view(M, self.r))
+            # T = A(x) only for the LoRA samples; the other samples see T rows that TMA zero-fills
+            T = self._new(lbn, Ho, Wo, self.r)
+            xl = xs if lbn == B else [x[:lbn] for x in xs]
+            srcs_l, prog_l = (srcs, prog) if lbn == B else self._conv_prog(xl, 3, stride, L.cin)
+            ops.gemm(srcs_l, [ops.bsrc(L.lora.a_fwd)], prog_l, lin=False, M=lbn * Ho * Wo, N=self.r,
+                     geo=(Wo, Ho), out=T.view(lbn * Ho * Wo, self.r))
             prog = prog + [(len(srcs), 1, 0, 0, 1, 0, 0)]
             srcs = srcs + [ops.asrc_nhwc(T)]
             bs.append(ops.bsrc(L.lora.sb_fwd))
@@ -231,7 +236,7 @@ class UNetB200:
                  rowvec=rowvec, residual=None if residual is None else residual.reshape(M, N),
                  round_bf16=out_fp32)
         if save is not None:
-            save.append(("conv3", name, xs, T, stride))
+            save.append(("conv3", name, xs if lbn == B else [x[:lbn] for x in xs], T, stride))
         return out
 
     def linear(self, name, xs, lora, residual=None, act=0, save=None):
@@ -245,16 +250,18 @@ class UNetB200:
             coff += x.shape[1]
         bs = [ops.bsrc(L.w_fwd)]
         T = None
+        Ml = self._lrows(M)
         if lora and L.lora is not None:
-            T = self._new(M, self.r)
-            ops.gemm(srcs, [ops.bsrc(L.lora.a_fwd)], prog, lin=True, M=M, N=self.r, out=T)
+            T = self._new(Ml, self.r)
+            srcs_l = srcs if Ml == M else [ops.asrc_mat(x[:Ml]) for x in xs]
+            ops.gemm(srcs_l, [ops.bsrc(L.lora.a_fwd)], prog, lin=True, M=Ml, N=self.r, out=T)
             prog = prog + [(len(srcs), 1, 0, 0, 1, 0, 0)]
-            srcs = srcs + [ops.asrc_mat(T)]
+            srcs = srcs + [ops.asrc_mat(T)]   # Ml rows: tiles past them read zeros (TMA bounds)
             bs.append(ops.bsrc(L.lora.sb_fwd))
         out = self._new(M, N)
         ops.gemm(srcs, bs, prog, lin=True, M=M, N=N, out=out, bias=L.bias, residual=residual, act=act)
         if save is not None:
-            save.append(("linear", name, xs, T))
+            save.append(("linear", name, xs if Ml == M else [x[:Ml] for x in xs], T))
         return out
 
     def gn(self, name, xs, B, HW, eps, silu, save=None):
@@ -265,7 +272,8 @@ class UNetB200:
         ops.groupnorm_fwd(xs[0], xs[1] if len(xs) > 1 else None, L.gamma, L.beta, eps, silu, out, stats,
                           B, HW, self.cfg.norm_num_groups)
         if save is not None:
-            save.append(("gn", name, xs, stats, eps, silu, B, HW))
+            lb = self._lrows(B)
+            save.append(("gn", name, xs if lb == B else [x[:lb * HW] for x in xs], stats[:lb], eps, silu, lb, HW))
         return out
 
     def ln(self, name, x, save=None):
@@ -274,7 +282,8 @@ class UNetB200:
         stats = self._new(x.shape[0], 2, dtype=torch.float32)
         ops.layernorm_fwd(x, L.gamma, L.beta, out, stats)
         if save is not None:
-            save.append(("ln", name, x, stats))
+            Ml = self._lrows(x.shape[0])
+            save.append(("ln", name, x[:Ml], stats[:Ml]))
         return out
 
     def attention(self, q, k, v, B, Sq, Skv, save=None):
@@ -284,7 +293,8 @@ class UNetB200:
         lse = self._new(B, Hh, Sq, dtype=torch.float32)
         ops.attn_fwd(q, k, v, out, lse, B, Hh, Sq, Skv, D, D ** -0.5)
         if save is not None:
-            save.append(("attn", q, k, v, out, lse, B, Sq, Skv))
+            lb = self._lrows(B)
+            save.append(("attn", q[:lb * Sq], k[:lb * Skv], v[:lb * Skv], out[:lb * Sq], lse[:lb], lb, Sq, Skv))
         return out
 
     # ------------------------------------------------------------------------------------
@@ -331,17 +341,28 @@ class UNetB200:
         gg = self._new(M, u.shape[1] // 2)
         ops.geglu_fwd(u, gg)
         if save is not None:
-            save.append(("geglu", u))
+            save.append(("geglu", u[:self._lrows(M)]))
         h = self.linear(t + ".ff.net.2", [gg], lora, residual=h, save=save)
         return self.linear(p + ".proj_out", [h], lora, residual=xf, save=save).view(B, H, W, C)
 
-    def forward(self, sample, timesteps, ctx, lora=True, save=False):
+    def _lrows(self, n):
+        """Rows / samples of an n-row (batch-major) tensor that belong to the LoRA samples."""
+        lb, bt = self._lb
+        return n * lb // bt
+
+    def forward(self, sample, timesteps, ctx, lora=True, save=False, lora_batch=None):
         """sample: fp32 [B,H,W,4] NHWC; timesteps: int64 [B]; ctx: bf16 [B*77, D].
-        Returns eps fp32 [B,H,W,4] (values rounded to bf16 like the autocast output)."""
+        Returns eps fp32 [B,H,W,4] (values rounded to bf16 like the autocast output).
+
+        lora_batch = b < B runs ONE pass in which only the first b samples carry the LoRA adapter
+        (student) and the rest see the frozen base weights (teacher): the adapter's T = A(x) is computed
+        for the leading rows only and the fused LoRA K-block reads zeros for the others.  The tape then
+        holds views of the first b samples, so backward() is the student's backward."""
         cfg = self.cfg
         lora = lora and self.has_lora
         tape = [] if save else None
         B, H, W, _ = sample.shape
+        self._lb = (lora_batch if (lora and lora_batch) else B, B)
         c0 = cfg.block_out_channels[0]
         emb = self._new(B, c0)
         ops.timestep_embed(timesteps, emb)
@@ -376,7 +397,7 @@ class UNetB200:
         g = self.gn("conv_norm_out", [x.view(Bx * Hx * Wx, Cx)], Bx, Hx * Wx, 1e-5, True, tape)
         eps = self.conv3("conv_out", [g.view(Bx, Hx, Wx, Cx)], False, out_fp32=True)
         if save:
-            self.saved = (tape, marks, (B, H, W))
+            self.saved = (tape, marks, (self._lb[0], H, W))
         return eps
 
     def _block(self, tape, marks, kind, name, x, aux, lora):
