@@ -104,6 +104,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_dkdv_tc_kernel(const 
   const uint32_t tmem_base = tmem_base_smem;
   griddep_sync();
 
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
   if (warp == 0) {
     if (lane == 0) {
       mbar_arrive_expect_tx(&kv_full, 2 * kBoxB);
@@ -124,10 +126,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_dkdv_tc_kernel(const 
       const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV);
       const uint32_t p_addr = smem_u32(sP), ds_addr = smem_u32(sdS);
       mbar_wait(&kv_ready, 0);  // K, V landed and their stray head columns are zeroed
-      for (int j = 0; j < ntiles; ++j) {
+      // S^T / dP^T of tile j+1 are issued as soon as the element-wise warps have copied tile j to
+      // registers, so the score GEMMs overlap the exp / dS math of the previous tile
+      auto issue_scores = [&](int j) {
         const int st = j % ST;
         mbar_wait(&q_full[st], (j / ST) & 1);
-        mbar_wait(&s_free, (j & 1) ^ 1);  // element-wise stage finished reading S^T / dP^T of tile j-1
+        mbar_wait(&s_free, (j & 1) ^ 1);
         tc_fence_after();
         const uint32_t q_addr = smem_u32(sQ + st * kBoxB), do_addr = smem_u32(sdO + st * kBoxB);
 #pragma unroll
@@ -138,6 +142,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_dkdv_tc_kernel(const 
                    umma_desc_sw128(do_addr + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
         }
         umma_commit(&s_full);
+      };
+      issue_scores(0);
+      for (int j = 0; j < ntiles; ++j) {
+        const int st = j % ST;
+        if (j + 1 < ntiles) issue_scores(j + 1);
+        const uint32_t q_addr = smem_u32(sQ + st * kBoxB), do_addr = smem_u32(sdO + st * kBoxB);
         mbar_wait(&p_full, j & 1);
         tc_fence_after();
 #pragma unroll
@@ -153,7 +163,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_dkdv_tc_kernel(const 
       }
       umma_commit(&acc_full);
     }
-  } else if (warp >= 4) {
+  }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
     // ===================== element-wise stage: thread = key row, warpgroup = column half ============
     const int g = (warp - 4) >> 2;
     const int qd = warp & 3;
@@ -192,27 +204,30 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_dkdv_tc_kernel(const 
       mbar_wait(&ld_full[st], (j / ST) & 1);
       mbar_wait(&s_full, j & 1);
       tc_fence_after();
+      // copy this warpgroup's 64 score / dP columns to registers, then hand the TMEM tiles back so
+      // the next tile's score GEMMs run under the math below
+      uint32_t sv[2][32], dv[2][32];
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        tmem_ld_32x32(tmem_base + lane_off + g * 64 + cc * 32, sv[cc]);
+        tmem_ld_32x32(tmem_base + 128 + lane_off + g * 64 + cc * 32, dv[cc]);
+      }
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&s_free);
       if (j > 0) mbar_wait(&p_free, (j - 1) & 1);  // previous P^T / dS^T consumed by the MMAs
 #pragma unroll
       for (int cc = 0; cc < 2; ++cc) {
         const int col0 = g * 64 + cc * 32;
-        uint32_t sv[32], dv[32];
-        tmem_ld_32x32(tmem_base + lane_off + col0, sv);
-        tmem_ld_32x32(tmem_base + 128 + lane_off + col0, dv);
-        tmem_ld_wait();
-        if (cc == 1) {
-          tc_fence_before();
-          mbar_arrive(&s_free);
-        }
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
           float pv[8], gv[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const int q = col0 + ch * 8 + e;
-            const float pe = kvalid ? fexp2(fmaf(__uint_as_float(sv[ch * 8 + e]), c, -sL[st * 128 + q])) : 0.f;
+            const float pe = kvalid ? fexp2(fmaf(__uint_as_float(sv[cc][ch * 8 + e]), c, -sL[st * 128 + q])) : 0.f;
             pv[e] = pe;
-            gv[e] = pe * (__uint_as_float(dv[ch * 8 + e]) - sD[st * 128 + q]);
+            gv[e] = pe * (__uint_as_float(dv[cc][ch * 8 + e]) - sD[st * 128 + q]);
           }
           st_operand_chunk(sP, row, (col0 >> 3) + ch, pv);
           st_operand_chunk(sdS, row, (col0 >> 3) + ch, gv);
@@ -311,6 +326,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_dq_tc_kernel(const __
   const uint32_t tmem_base = tmem_base_smem;
   griddep_sync();
 
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
   if (warp == 0) {
     if (lane == 0) {
       mbar_arrive_expect_tx(&q_full, 2 * kBoxB);
@@ -330,7 +347,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_dq_tc_kernel(const __
       const uint32_t idesc_g = umma_idesc_bf16(128, DP, 0, 1);  // B = K MN-major
       const uint32_t q_addr = smem_u32(sQ), do_addr = smem_u32(sdO), ds_addr = smem_u32(sdS);
       mbar_wait(&q_ready, 0);  // Q, dO landed and their stray head columns are zeroed
-      for (int j = 0; j < ntiles; ++j) {
+      auto issue_scores = [&](int j) {
         const int st = j % ST;
         mbar_wait(&kv_full[st], (j / ST) & 1);
         mbar_wait(&s_free, (j & 1) ^ 1);
@@ -344,6 +361,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_dq_tc_kernel(const __
                    umma_desc_sw128(v_addr + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
         }
         umma_commit(&s_full);
+      };
+      issue_scores(0);
+      for (int j = 0; j < ntiles; ++j) {
+        const int st = j % ST;
+        if (j + 1 < ntiles) issue_scores(j + 1);
+        const uint32_t k_addr = smem_u32(sK + st * kBoxB);
         mbar_wait(&p_full, j & 1);
         tc_fence_after();
 #pragma unroll
@@ -356,7 +379,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_dq_tc_kernel(const __
       }
       umma_commit(&acc_full);
     }
-  } else if (warp >= 4) {
+  }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
     const int g = (warp - 4) >> 2;
     const int qd = warp & 3;
     const int row = qd * 32 + lane;
@@ -383,26 +408,27 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_dq_tc_kernel(const __
     for (int j = 0; j < ntiles; ++j) {
       mbar_wait(&s_full, j & 1);
       tc_fence_after();
+      uint32_t sv[2][32], dv[2][32];
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        tmem_ld_32x32(tmem_base + lane_off + g * 64 + cc * 32, sv[cc]);
+        tmem_ld_32x32(tmem_base + 128 + lane_off + g * 64 + cc * 32, dv[cc]);
+      }
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&s_free);
       if (j > 0) mbar_wait(&p_free, (j - 1) & 1);
 #pragma unroll
       for (int cc = 0; cc < 2; ++cc) {
         const int col0 = g * 64 + cc * 32;
-        uint32_t sv[32], dv[32];
-        tmem_ld_32x32(tmem_base + lane_off + col0, sv);
-        tmem_ld_32x32(tmem_base + 128 + lane_off + col0, dv);
-        tmem_ld_wait();
-        if (cc == 1) {
-          tc_fence_before();
-          mbar_arrive(&s_free);
-        }
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
           float gv[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const int key = j * 128 + col0 + ch * 8 + e;
-            const float pe = key < p.Skv ? fexp2(fmaf(__uint_as_float(sv[ch * 8 + e]), c, -lrow)) : 0.f;
-            gv[e] = pe * (__uint_as_float(dv[ch * 8 + e]) - drow);
+            const float pe = key < p.Skv ? fexp2(fmaf(__uint_as_float(sv[cc][ch * 8 + e]), c, -lrow)) : 0.f;
+            gv[e] = pe * (__uint_as_float(dv[cc][ch * 8 + e]) - drow);
           }
           st_operand_chunk(sdS, row, (col0 >> 3) + ch, gv);
         }
