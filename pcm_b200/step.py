@@ -154,9 +154,8 @@ class PCMTrainStep:
 
     def capture(self, warmup=2):
         """Capture the iteration into CUDA graph(s) after eager warm-up runs.  Single GPU: one graph
-        for forward + backward + optimiser.  Data parallel: the NCCL all-reduce is captured inside
-        the same graph when the installed NCCL supports it, otherwise the step is split into
-        graph(forward+backward) -> eager all-reduce -> graph(optimiser)."""
+        for forward + backward + optimiser.  Data parallel: graph(forward+backward) -> eager NCCL
+        all-reduce -> graph(optimiser) (PCM_NCCL_IN_GRAPH=1 captures the collective too)."""
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         snap = (self.unet.lora_master.clone(), self.exp_avg.clone(), self.exp_avg_sq.clone(),
@@ -168,16 +167,14 @@ class PCMTrainStep:
         torch.cuda.synchronize()
         self.graph, self.graph_opt = None, None
         n0 = ops.LAUNCHES["count"]
-        try:
+        if self.world == 1 or os.environ.get("PCM_NCCL_IN_GRAPH", "0") == "1":
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 self.run_eager()
             self.graph = g
-        except Exception:
-            if self.world == 1:
-                raise
-            torch.cuda.synchronize()
-            n0 = ops.LAUNCHES["count"]
+        else:
+            # data parallel: keep the collective outside the graphs (robust across NCCL versions):
+            # graph(forward + backward) -> eager all_reduce -> graph(clip + AdamW + LoRA refresh)
             g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
             with torch.cuda.graph(g1):
                 self.forward_backward()
