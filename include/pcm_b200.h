@@ -19,7 +19,7 @@ extern "C" {
 #endif
 
 #define PCM_MAX_ASRC 6
-#define PCM_MAX_BSRC 2
+#define PCM_MAX_BSRC 4
 #define PCM_MAX_PROG 24
 
 /* A-operand source: a bf16 NHWC tensor viewed as (C, W, H, B) with element strides. */
@@ -39,7 +39,10 @@ typedef struct {
 /* One K-program entry: nchunks consecutive 64-wide K blocks read from a[a_src] at channel a_c0..,
  * spatially shifted by (dw, dh) (zero filled outside the image), against b[b_src] columns b_k0... */
 typedef struct {
-  int32_t a_src, b_src, dw, dh, nchunks, a_c0, b_k0, pad_;
+  int32_t a_src, b_src, dw, dh, nchunks, a_c0, b_k0;
+  uint16_t n_lo, n_hi; /* n_hi > 0: the entry only contributes to output columns [n_lo, n_hi)
+                         (multiples of block_n) - lets one launch run several Linear layers that
+                         share their input (q/k/v) with per-layer LoRA K blocks */
 } pcm_kentry;
 
 /* Implicit-GEMM descriptor: out[m, n] = alpha * sum_k A[m, k] * Bw[n, k] (+bias +rowvec +residual).

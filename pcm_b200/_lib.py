@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libpcm_b200.so")
 
-MAX_ASRC, MAX_BSRC, MAX_PROG = 6, 2, 24
+MAX_ASRC, MAX_BSRC, MAX_PROG = 6, 4, 24
 
 
 class ASrc(C.Structure):
@@ -23,7 +23,7 @@ class BSrc(C.Structure):
 
 class KEntry(C.Structure):
     _fields_ = [("a_src", C.c_int32), ("b_src", C.c_int32), ("dw", C.c_int32), ("dh", C.c_int32),
-                ("nchunks", C.c_int32), ("a_c0", C.c_int32), ("b_k0", C.c_int32), ("pad_", C.c_int32)]
+                ("nchunks", C.c_int32), ("a_c0", C.c_int32), ("b_k0", C.c_int32), ("n_lo", C.c_uint16), ("n_hi", C.c_uint16)]
 
 
 class GemmDesc(C.Structure):

@@ -7,7 +7,8 @@
 namespace pcm {
 
 struct KEntry {
-  int a_map, b_map, dw, dh, nchunks, a_c0, b_k0, pad_;
+  int a_map, b_map, dw, dh, nchunks, a_c0, b_k0;
+  unsigned short n_lo, n_hi;  // n_hi > 0: entry applies to tiles with n_lo <= n0 < n_hi only
 };
 
 struct alignas(64) GemmParams {
@@ -27,6 +28,7 @@ struct alignas(64) GemmParams {
   int out_fp32, round_bf16;
   float alpha;
   int act;
+  int filtered;      // some K entries carry an N range (per-tile K-block count varies)
   int ksplit;        // > 1: work item = (tile, K split); fp32 partial sums are atomically added
   float* ws;         // into ws[m * N + n]; bias / residual / activation run in the finalize kernel
 };

@@ -88,6 +88,7 @@ pcm_gemm_kernel(const __grid_constant__ GemmParams p) {
         int kidx = 0;
         for (int e = 0; e < p.num_prog; ++e) {
           const KEntry en = p.prog[e];
+          if (en.n_hi != 0 && (n0 < en.n_lo || n0 >= en.n_hi)) continue;  // other layer's K block
           if (kidx + en.nchunks <= kb0 || kidx >= kb1) {  // entry entirely outside this K split
             kidx += en.nchunks;
             continue;
@@ -122,7 +123,15 @@ pcm_gemm_kernel(const __grid_constant__ GemmParams p) {
       uint32_t acc_phase = 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
         const int ks = item % p.ksplit;
-        const int nkb = min(p.num_kblocks, (ks + 1) * kb_per) - ks * kb_per;
+        int nkb = min(p.num_kblocks, (ks + 1) * kb_per) - ks * kb_per;
+        if (p.filtered) {  // N-ranged entries (ksplit == 1): count the K blocks of this tile
+          const int n0 = (item % p.tiles_n) * p.block_n;
+          nkb = 0;
+          for (int e = 0; e < p.num_prog; ++e) {
+            const KEntry en = p.prog[e];
+            if (en.n_hi == 0 || (n0 >= en.n_lo && n0 < en.n_hi)) nkb += en.nchunks;
+          }
+        }
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256;
@@ -409,8 +418,13 @@ static int launch_gemm(const pcm_gemm_desc* d, cudaStream_t stream) {
     const pcm_kentry& k = d->prog[e];
     if (k.a_src < 0 || k.a_src >= d->num_a || k.b_src < 0 || k.b_src >= d->num_b || k.nchunks < 1)
       return set_error("pcm_gemm: bad K program entry");
-    p.prog[e] = KEntry{k.a_src, k.b_src, k.dw, k.dh, k.nchunks, k.a_c0, k.b_k0, 0};
+    p.prog[e] = KEntry{k.a_src, k.b_src, k.dw, k.dh, k.nchunks, k.a_c0, k.b_k0, k.n_lo, k.n_hi};
     nkb += k.nchunks;
+    if (k.n_hi != 0) {
+      if (k.n_lo % d->block_n != 0 || (k.n_hi % d->block_n != 0 && k.n_hi < d->N) || k.n_hi <= k.n_lo)
+        return set_error("pcm_gemm: K entry N range must be aligned to block_n");
+      p.filtered = 1;
+    }
   }
   p.num_prog = d->num_prog;
   p.lin = d->lin;
@@ -441,7 +455,7 @@ static int launch_gemm(const pcm_gemm_desc* d, cudaStream_t stream) {
   p.act = d->act;
   p.ksplit = 1;
   p.ws = nullptr;
-  if (d->ksplit > 1 && d->splitk_ws != nullptr) {
+  if (d->ksplit > 1 && d->splitk_ws != nullptr && !p.filtered) {
     int ks = d->ksplit;
     if (ks > nkb) ks = nkb;
     const int per = (nkb + ks - 1) / ks;
@@ -474,7 +488,7 @@ static int launch_gemm(const pcm_gemm_desc* d, cudaStream_t stream) {
     CUDA_TRY(launch_pdl(splitk_finalize_kernel, dim3(fg), dim3(256), 0, stream, f));
     return 0;
   }
-  {
+  if (!p.filtered) {
     const int rc2 = launch_gemm2(p, d, stream);  // 2-CTA kernel for the large layers
     if (rc2 <= 0) return rc2;
   }

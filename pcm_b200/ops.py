@@ -87,7 +87,8 @@ def pick_tiling(M, N, nkb):
 def gemm(a_srcs, b_srcs, prog, *, lin, M, N, out, geo=(1, 1), bias=None, rowvec=None,
          residual=None, out_strides=None, epi=None, alpha=1.0, act=0, round_bf16=False,
          block_n=None, ksplit=None):
-    """Launch the tcgen05 implicit GEMM.  prog: list of (a_src, b_src, dw, dh, nchunks, a_c0, b_k0).
+    """Launch the tcgen05 implicit GEMM.  prog: list of (a_src, b_src, dw, dh, nchunks, a_c0, b_k0
+    [, n_lo, n_hi]); an entry with n_hi > 0 only feeds output columns [n_lo, n_hi).
 
     out: bf16 or fp32 tensor; rows are addressed as b*osB + h*osH + w*osW with (osW, osH, osB) =
     out_strides (default: dense [M, ld] with ld = out.stride(-2))."""
@@ -97,11 +98,14 @@ def gemm(a_srcs, b_srcs, prog, *, lin, M, N, out, geo=(1, 1), bias=None, rowvec=
     for i, b in enumerate(b_srcs):
         d.b[i] = b
     for i, e in enumerate(prog):
-        d.prog[i] = L.KEntry(*e, 0)
+        d.prog[i] = L.KEntry(*e[:7], *(e[7:9] if len(e) > 7 else (0, 0)))
     d.num_a, d.num_b, d.num_prog = len(a_srcs), len(b_srcs), len(prog)
     d.lin, d.M, d.N = int(lin), M, N
     d.geoW, d.geoH = geo
     nkb = sum(e[4] for e in prog)
+    if any(len(e) > 7 and e[8] for e in prog):
+        ksplit = 1
+        assert block_n is not None
     if block_n is None and ksplit is None:
         block_n, ksplit = pick_tiling(M, N, nkb)
     d.block_n = block_n or pick_block_n(M, N)

@@ -12,6 +12,8 @@ teacher, :1263-1268 target) and its autograd backward (:1296), with:
 Parameters use diffusers state-dict names; LoRA factors live in ONE flat fp32 buffer
 (`lora_master`), their gradients in `lora_grad`.
 """
+import types
+
 import torch
 
 from . import ops
@@ -24,7 +26,8 @@ _S2 = ((1, -1), (0, 0), (1, 0))
 
 
 class _Lora:
-    __slots__ = ("a_off", "b_off", "a_fwd", "sb_fwd", "sb_t", "a_t", "gA", "gB", "opnd_off")
+    __slots__ = ("a_off", "b_off", "a_fwd", "sb_fwd", "sb_t", "a_t", "gA", "gB", "opnd_off",
+                 "o_a_fwd", "o_sb_fwd", "o_sb_t", "o_a_t")
 
 
 class _Layer:
@@ -90,12 +93,31 @@ class UNetB200:
             self.lora_master = torch.cat(master).to(device)
             self.lora_grad = torch.zeros_like(self.lora_master)
             self.lora_opnd = torch.empty(opnd_total, device=device, dtype=BF16)
+            # operand copies: [A | s*B | (s*B)^T | A^T] per layer; the layers of a shared-input group
+            # (attn1 q/k/v, attn2 k/v) are laid out kind-major so that their A, s*B and (s*B)^T
+            # copies stack into single GEMM operands
+            by_name = {L.name: (L, taps) for L, taps in entries}
+            units, seen = [], set()
+            for L, taps in entries:
+                if L.name in seen:
+                    continue
+                grp = self._group_of(L.name)
+                members = [by_name[n] for n in grp] if grp and all(n in by_name for n in grp) else [(L, taps)]
+                seen.update(m[0].name for m in members)
+                units.append(members)
+            o = 0
+            for members in units:
+                for kind in ("a_fwd", "sb_fwd", "sb_t", "a_t"):
+                    for L, taps in members:
+                        n = self.r * taps * L.cin if kind in ("a_fwd", "a_t") else L.cout * self.r
+                        setattr(L.lora, "o_" + kind, o)
+                        o += n
+            assert o == opnd_total
             rows, work = [], 0
             for L, taps in entries:
                 lo = L.lora
                 na, nb = self.r * taps * L.cin, L.cout * self.r
-                o = lo.opnd_off
-                a_fwd, sb_fwd, sb_t, a_t = o, o + na, o + na + nb, o + na + 2 * nb
+                a_fwd, sb_fwd, sb_t, a_t = lo.o_a_fwd, lo.o_sb_fwd, lo.o_sb_t, lo.o_a_t
                 lo.a_fwd = self.lora_opnd[a_fwd:a_fwd + na].view(self.r, taps * L.cin)
                 lo.sb_fwd = self.lora_opnd[sb_fwd:sb_fwd + nb].view(L.cout, self.r)
                 lo.sb_t = self.lora_opnd[sb_t:sb_t + nb].view(self.r, L.cout)
@@ -109,6 +131,7 @@ class UNetB200:
             self.refresh_table = torch.tensor(rows, dtype=torch.int64, device=device)
             self.refresh_work = work
             self.refresh_lora()
+        self._build_groups(need_backward)
         self.saved = None
         self._lb = (1, 1)
         # LoRA weight-gradient GEMMs are off the dgrad critical path (they only feed the optimiser):
@@ -118,6 +141,50 @@ class UNetB200:
                             _os.environ.get("PCM_WGRAD_STREAM", "1") != "0")
         self.wstream = torch.cuda.Stream(device=device) if self.use_wstream else None
         self._keep = []
+
+    _GROUPS = ((".attn1.to_q", (".attn1.to_q", ".attn1.to_k", ".attn1.to_v")),
+               (".attn2.to_k", (".attn2.to_k", ".attn2.to_v")))
+
+    @classmethod
+    def _group_of(cls, name):
+        """Names of the shared-input Linear group `name` belongs to (attn1 q/k/v, attn2 k/v), or None."""
+        for _, sufs in cls._GROUPS:
+            for suf in sufs:
+                if name.endswith(suf):
+                    return [name[:-len(suf)] + x for x in sufs]
+        return None
+
+    def _build_groups(self, need_backward):
+        """Stack the frozen weights (and view the kind-major LoRA operand copies) of every shared-input
+        group so that q/k/v (resp. cross-attention k/v) run as ONE GEMM with N = g*C."""
+        self.groups = {}
+        for name in list(self.layers):
+            for lead, _ in self._GROUPS:
+                if not name.endswith(lead):
+                    continue
+                names = self._group_of(name)
+                Ls = [self.layers[n] for n in names]
+                assert all(L.bias is None and L.cin == Ls[0].cin and L.cout == Ls[0].cout for L in Ls)
+                G = types.SimpleNamespace(names=names, layers=Ls, g=len(Ls), cin=Ls[0].cin, cout=Ls[0].cout)
+                G.w_stack = torch.cat([L.w_fwd for L in Ls], 0).contiguous()
+                G.w_t_cat = None
+                if all(L.w_t is not None for L in Ls):
+                    G.w_t_cat = torch.cat([L.w_t for L in Ls], 1).contiguous()   # [cin, g*C]
+                for i, L in enumerate(Ls):
+                    L.w_fwd = G.w_stack[i * G.cout:(i + 1) * G.cout]
+                    L.w_t = None
+                G.lora = all(L.lora is not None for L in Ls)
+                if G.lora:
+                    r, g = self.r, G.g
+                    lo0 = Ls[0].lora
+                    op = self.lora_opnd
+                    G.a_stack = op[lo0.o_a_fwd:lo0.o_a_fwd + g * r * G.cin].view(g * r, G.cin)
+                    G.sb_stack = op[lo0.o_sb_fwd:lo0.o_sb_fwd + g * G.cout * r].view(g * G.cout, r)
+                    G.sbt_stack = op[lo0.o_sb_t:lo0.o_sb_t + g * G.cout * r].view(g * r, G.cout)
+                    assert Ls[-1].lora.a_fwd.data_ptr() == G.a_stack[(g - 1) * r:].data_ptr()
+                    assert Ls[-1].lora.sb_fwd.data_ptr() == G.sb_stack[(g - 1) * G.cout:].data_ptr()
+                    assert Ls[-1].lora.sb_t.data_ptr() == G.sbt_stack[(g - 1) * r:].data_ptr()
+                self.groups[name] = G
 
     class _Side:
         """Run the enclosed launches on the wgrad side stream, ordered after everything enqueued so far
@@ -264,6 +331,30 @@ class UNetB200:
             save.append(("linear", name, xs if Ml == M else [x[:Ml] for x in xs], T))
         return out
 
+    def linear_group(self, lead, x, lora, save=None):
+        """The g Linear layers of a shared-input group (attn1 q/k/v, attn2 k/v) as ONE GEMM:
+        out[M, g*C] = x @ [W_0; ...; W_g-1]^T, layer i's LoRA up-projection entering as a K block that
+        only feeds its own C output columns.  Returns the g column views of out."""
+        G = self.groups[lead]
+        g, Cc, r = G.g, G.cout, self.r
+        M = x.shape[0]
+        Ml = self._lrows(M)
+        srcs, bs = [ops.asrc_mat(x)], [ops.bsrc(G.w_stack)]
+        prog = [(0, 0, 0, 0, G.cin // 64, 0, 0)]
+        T = None
+        bn = 160 if Cc % 160 == 0 else 64
+        if lora and G.lora:
+            T = self._new(Ml, g * r)
+            ops.gemm([ops.asrc_mat(x[:Ml])], [ops.bsrc(G.a_stack)], prog, lin=True, M=Ml, N=g * r, out=T)
+            srcs.append(ops.asrc_mat(T))
+            bs.append(ops.bsrc(G.sb_stack))
+            prog = prog + [(1, 1, 0, 0, 1, i * r, 0, i * Cc, (i + 1) * Cc) for i in range(g)]
+        out = self._new(M, g * Cc)
+        ops.gemm(srcs, bs, prog, lin=True, M=M, N=g * Cc, out=out, block_n=bn)
+        if save is not None:
+            save.append(("lgroup", lead, x[:Ml], T))
+        return [out[:, i * Cc:(i + 1) * Cc] for i in range(g)]
+
     def gn(self, name, xs, B, HW, eps, silu, save=None):
         L = self.layers[name]
         C = sum(x.shape[-1] for x in xs)
@@ -289,7 +380,7 @@ class UNetB200:
     def attention(self, q, k, v, B, Sq, Skv, save=None):
         Hh = self.cfg.num_heads
         D = q.shape[1] // Hh
-        out = torch.empty_like(q)
+        out = self._new(q.shape[0], q.shape[1])
         lse = self._new(B, Hh, Sq, dtype=torch.float32)
         ops.attn_fwd(q, k, v, out, lse, B, Hh, Sq, Skv, D, D ** -0.5)
         if save is not None:
@@ -325,15 +416,12 @@ class UNetB200:
         g = self.gn(p + ".norm", [xf], B, S, 1e-6, False, save)
         h = self.linear(p + ".proj_in", [g], lora, save=save)
         n = self.ln(t + ".norm1", h, save)
-        q = self.linear(t + ".attn1.to_q", [n], lora, save=save)
-        k = self.linear(t + ".attn1.to_k", [n], lora, save=save)
-        v = self.linear(t + ".attn1.to_v", [n], lora, save=save)
+        q, k, v = self.linear_group(t + ".attn1.to_q", n, lora, save=save)
         a = self.attention(q, k, v, B, S, S, save)
         h = self.linear(t + ".attn1.to_out.0", [a], lora, residual=h, save=save)
         n = self.ln(t + ".norm2", h, save)
         q = self.linear(t + ".attn2.to_q", [n], lora, save=save)
-        k = self.linear(t + ".attn2.to_k", [ctx], lora, save=save)
-        v = self.linear(t + ".attn2.to_v", [ctx], lora, save=save)
+        k, v = self.linear_group(t + ".attn2.to_k", ctx, lora, save=save)
         a = self.attention(q, k, v, B, S, ctx.shape[0] // B, save)
         h = self.linear(t + ".attn2.to_out.0", [a], lora, residual=h, save=save)
         n = self.ln(t + ".norm3", h, save)
@@ -460,6 +548,38 @@ class UNetB200:
         ops.gemm(srcs, bs, prog, lin=True, M=M, N=L.cin, out=dx, residual=accumulate)
         return dx
 
+    def linear_group_bwd(self, rec, dpk, need_dx=True):
+        """rec = ("lgroup", lead, x, T); dpk [M, g*C] = the g output gradients side by side.
+        Returns dx [M, cin] (or None): ONE dgrad GEMM over K = g*C (+ the g LoRA blocks)."""
+        _, lead, x, T = rec
+        G = self.groups[lead]
+        g, Cc, r = G.g, G.cout, self.r
+        M = dpk.shape[0]
+        dT = None
+        if T is not None:
+            dT = self._new(M, g * r)
+            prog = [(0, 0, 0, 0, Cc // 64, i * Cc, 0, i * r, (i + 1) * r) for i in range(g)]
+            ops.gemm([ops.asrc_mat(dpk)], [ops.bsrc(G.sbt_stack)], prog, lin=True, M=M, N=g * r, out=dT,
+                     block_n=64)
+            with UNetB200._Side(self, (dpk, T, dT, x)):
+                for i, L in enumerate(G.layers):
+                    ops.wgrad(ops.asrc_mat(dpk[:, i * Cc:(i + 1) * Cc]), ops.asrc_mat(T), L.lora.gB, lin=True,
+                              M=M, os_row=r, os_col=1, alpha=self.scale, q_c0=i * r)
+                    ops.wgrad(ops.asrc_mat(x), ops.asrc_mat(dT), L.lora.gA, lin=True, M=M, os_row=1,
+                              os_col=G.cin, q_c0=i * r)
+        if not need_dx:
+            return None
+        srcs, bs = [ops.asrc_mat(dpk)], [ops.bsrc(G.w_t_cat)]
+        prog = [(0, 0, 0, 0, g * Cc // 64, 0, 0)]
+        if dT is not None:
+            srcs.append(ops.asrc_mat(dT))
+            for i, L in enumerate(G.layers):
+                bs.append(ops.bsrc(L.lora.a_t))
+                prog.append((1, 1 + i, 0, 0, 1, i * r, 0))
+        dx = self._new(M, G.cin)
+        ops.gemm(srcs, bs, prog, lin=True, M=M, N=G.cin, out=dx)
+        return dx
+
     def conv3_bwd(self, rec, dy, need_dx=True, accumulate=None):
         """rec = ("conv3", name, xs, T, stride); dy [B,Ho,Wo,N].  Returns dx [B,H,W,cin_total]."""
         _, name, xs, T, stride = rec
@@ -557,10 +677,17 @@ class UNetB200:
         _, q, k, v, out, lse, B, Sq, Skv = rec
         Hh = self.cfg.num_heads
         D = q.shape[1] // Hh
-        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        Cc = q.shape[1]
+        if q.stride(0) == 3 * Cc:     # self-attention: q/k/v are column views of one [M, 3C] matrix
+            pk = self._new(q.shape[0], 3 * Cc)
+            dq, dk, dv = pk[:, :Cc], pk[:, Cc:2 * Cc], pk[:, 2 * Cc:]
+        else:                         # cross-attention: k/v views of one [B*77, 2C] matrix
+            dq = self._new(q.shape[0], Cc)
+            pk = self._new(k.shape[0], 2 * Cc)
+            dk, dv = pk[:, :Cc], pk[:, Cc:]
         delta = torch.empty_like(lse)
         ops.attn_bwd(q, k, v, out, dout, lse, delta, dq, dk, dv, B, Hh, Sq, Skv, D, D ** -0.5)
-        return dq, dk, dv
+        return dq, pk
 
     # ------------------------------------------------------------------------------------
     # block backward (records were appended in forward order)
@@ -589,7 +716,7 @@ class UNetB200:
 
     def transformer_bwd(self, recs, dout):
         """recs order as appended by transformer(); dout [B,H,W,C]; returns dx [B,H,W,C]."""
-        (gn, pin, ln1, lq, lk, lv, at1, lo1, ln2, lq2, lk2, lv2, at2, lo2, ln3, ff1, gegl, ff2, pout) = recs
+        (gn, pin, ln1, lqkv, at1, lo1, ln2, lq2, lkv2, at2, lo2, ln3, ff1, gegl, ff2, pout) = recs
         B, H, W, C = dout.shape
         M = B * H * W
         do = dout.view(M, C)
@@ -601,16 +728,13 @@ class UNetB200:
         dn3 = self.linear_bwd(ff1, du)
         dh2 = self.ln_bwd(ln3, dn3, add=dh3)
         da2 = self.linear_bwd(lo2, dh2)
-        dq2, dk2, dv2 = self.attn_bwd(at2, da2)
-        self.linear_bwd(lk2, dk2, need_dx=False)
-        self.linear_bwd(lv2, dv2, need_dx=False)
+        dq2, dkv2 = self.attn_bwd(at2, da2)
+        self.linear_group_bwd(lkv2, dkv2, need_dx=False)
         dn2 = self.linear_bwd(lq2, dq2)
         dh1 = self.ln_bwd(ln2, dn2, add=dh2)
         da1 = self.linear_bwd(lo1, dh1)
-        dq, dk, dv = self.attn_bwd(at1, da1)
-        dn1 = self.linear_bwd(lq, dq)
-        dn1 = self.linear_bwd(lk, dk, accumulate=dn1)
-        dn1 = self.linear_bwd(lv, dv, accumulate=dn1)
+        _, dqkv = self.attn_bwd(at1, da1)
+        dn1 = self.linear_group_bwd(lqkv, dqkv)
         dh0 = self.ln_bwd(ln1, dn1, add=dh1)
         dg = self.linear_bwd(pin, dh0)
         dx, _ = self.gn_bwd(gn, dg, add=do)

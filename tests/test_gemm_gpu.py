@@ -150,3 +150,42 @@ def test_conv3x3_splitk(cuda, B, H, W, Cin, Cout):
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias, padding=1)
     ref = F.silu(ref + rowvec.float()[:, :, None, None] + res.float().permute(0, 3, 1, 2))
     _close(out.permute(0, 3, 1, 2), ref)
+
+
+@pytest.mark.parametrize("M,Ml,K,C,g", [(1848, 616, 768, 320, 2), (4096, 2048, 320, 320, 3), (300, 300, 128, 64, 3)])
+def test_grouped_linear_n_ranges(cuda, M, Ml, K, C, g):
+    """g Linear layers sharing their input as one GEMM (N = g*C): per-layer LoRA K blocks restricted
+    to their own output columns by N-ranged K entries; only the first Ml rows carry the adapter
+    (T has Ml rows, the rest is TMA zero fill); 4 B sources in the dgrad-style second launch."""
+    from pcm_b200 import ops
+    x = _rand((M, K), cuda, 1)
+    w = _rand((g * C, K), cuda, 2, K ** -0.5)
+    T = _rand((Ml, g * 64), cuda, 3)
+    sb = _rand((g * C, 64), cuda, 4, 0.1)
+    bn = 160 if C % 160 == 0 else 64
+    prog = [(0, 0, 0, 0, K // 64, 0, 0)] + [(1, 1, 0, 0, 1, i * 64, 0, i * C, (i + 1) * C) for i in range(g)]
+    out = torch.empty(M, g * C, device=cuda, dtype=torch.bfloat16)
+    ops.gemm([ops.asrc_mat(x), ops.asrc_mat(T)], [ops.bsrc(w), ops.bsrc(sb)], prog, lin=True, M=M, N=g * C,
+             out=out, block_n=bn)
+    ref = F.linear(x.float(), w.float())
+    for i in range(g):
+        ref[:Ml, i * C:(i + 1) * C] += T[:, i * 64:(i + 1) * 64].float() @ sb[i * C:(i + 1) * C].float().t()
+    _close(out, ref)
+    # N-ranged A column blocks (the dT = dy_i @ (sB_i) launch) reading column views of `out`
+    sbt = _rand((g * 64, C), cuda, 5, C ** -0.5)
+    dT = torch.empty(M, g * 64, device=cuda, dtype=torch.bfloat16)
+    prog = [(0, 0, 0, 0, C // 64, i * C, 0, i * 64, (i + 1) * 64) for i in range(g)]
+    ops.gemm([ops.asrc_mat(out)], [ops.bsrc(sbt)], prog, lin=True, M=M, N=g * 64, out=dT, block_n=64)
+    ref2 = torch.cat([out[:, i * C:(i + 1) * C].float() @ sbt[i * 64:(i + 1) * 64].float().t() for i in range(g)], 1)
+    _close(dT, ref2)
+    # 1 + g B sources
+    wt = _rand((K, g * C), cuda, 6, (g * C) ** -0.5)
+    ats = [_rand((K, 64), cuda, 7 + i, 0.1) for i in range(g)]
+    prog = [(0, 0, 0, 0, g * C // 64, 0, 0)] + [(1, 1 + i, 0, 0, 1, i * 64, 0) for i in range(g)]
+    dx = torch.empty(M, K, device=cuda, dtype=torch.bfloat16)
+    ops.gemm([ops.asrc_mat(out), ops.asrc_mat(dT)], [ops.bsrc(wt)] + [ops.bsrc(a) for a in ats], prog, lin=True,
+             M=M, N=K, out=dx)
+    ref3 = out.float() @ wt.float().t()
+    for i in range(g):
+        ref3 += dT[:, i * 64:(i + 1) * 64].float() @ ats[i].float().t()
+    _close(dx, ref3)
