@@ -19,6 +19,9 @@ SHAPES = [  # (kind, M|(B,H,W), K|Cin, N, residual)
     ("conv", (8, 8, 8), 1280, 1280, True),
     ("lin", 8192, 640, 5120, False),
     ("lin", 32768, 1280, 320, True),
+    ("lin", 98304, 384, 320, True),
+    ("lin", 98304, 384, 2560, False),
+    ("lin", 24576, 704, 640, True),
 ]
 sel = [int(a) for a in sys.argv[1:]] or range(len(SHAPES))
 iters = int(os.environ.get("ITERS", "20"))
