@@ -185,34 +185,36 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc_kernel(const __grid
       tc_fence_before();
       mbar_arrive(&s_free[st]);  // buffer st may be overwritten by QK^T of tile j + 2
       const int kbase = j * 128;
-      float mx = -INFINITY;
+      // 4 independent max / sum chains: a single 128-long dependent chain costs ~4 cycles per link
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
       for (int i = 0; i < 128; ++i) {
         s[i] = (kbase + i < p.Skv) ? s[i] * c : -INFINITY;
-        mx = fmaxf(mx, s[i]);
+        mx4[i & 3] = fmaxf(mx4[i & 3], s[i]);
       }
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       const float m_new = fmaxf(m_run, mx);
       const float alpha = fast_exp2(m_run - m_new);
       m_run = m_new;
-      float rs = 0.f;
+      float rs4[4] = {0.f, 0.f, 0.f, 0.f};
       if (j > 0) mbar_wait(&p_free, (j - 1) & 1);  // PV of tile j-1 finished reading P
+      const uint32_t sp_row = smem_u32(sP) + row * 128;
 #pragma unroll
       for (int ch = 0; ch < 16; ++ch) {
         float pv[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           pv[e] = fast_exp2(s[ch * 8 + e] - m_new);
-          rs += pv[e];
+          rs4[e & 3] += pv[e];
         }
         uint4 u;
         u.x = pack_bf16x2(pv[0], pv[1]);
         u.y = pack_bf16x2(pv[2], pv[3]);
         u.z = pack_bf16x2(pv[4], pv[5]);
         u.w = pack_bf16x2(pv[6], pv[7]);
-        uint8_t* dst = sP + (ch >> 3) * kBoxBytes + row * 128 + (((ch & 7) ^ (row & 7)) << 4);
-        *reinterpret_cast<uint4*>(dst) = u;
+        sts128(sp_row + (ch >> 3) * kBoxBytes + (((ch & 7) ^ (row & 7)) << 4), u.x, u.y, u.z, u.w);
       }
-      l_run = l_run * alpha + rs;
+      l_run = l_run * alpha + ((rs4[0] + rs4[1]) + (rs4[2] + rs4[3]));
       fence_proxy_async();
       mbar_arrive(&p_full);
       // fold the previous tile's O (computed against the previous max) into the accumulator
@@ -448,32 +450,34 @@ __global__ void __launch_bounds__(kV2Threads, 1) attn_fwd_tc2_kernel(const __gri
         for (int i = 0; i < 128; ++i)
           if (kbase + i >= p.Skv) s[i] = -INFINITY;
       }
-      float mx = s[0];
+      // 4 independent max / sum chains: a single 128-long dependent chain costs ~4 cycles per link
+      float mx4[4] = {s[0], s[1], s[2], s[3]};
 #pragma unroll
-      for (int i = 1; i < 128; ++i) mx = fmaxf(mx, s[i]);
+      for (int i = 4; i < 128; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], s[i]);
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       const float m_new = fmaxf(m_run, mx);        // raw-score domain (c > 0)
       const float alpha = fast_exp2((m_run - m_new) * c);
       m_run = m_new;
       const float mc = m_new * c;
-      float rs = 0.f;
+      float rs4[4] = {0.f, 0.f, 0.f, 0.f};
       if (j > 0) mbar_wait(&p_free[t], (j - 1) & 1);
+      const uint32_t sp_row = smem_u32(sPt) + row * 128;
 #pragma unroll
       for (int ch = 0; ch < 16; ++ch) {
         float pv[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           pv[e] = fast_exp2(fmaf(s[ch * 8 + e], c, -mc));
-          rs += pv[e];
+          rs4[e & 3] += pv[e];
         }
         uint4 u;
         u.x = pack_bf16x2(pv[0], pv[1]);
         u.y = pack_bf16x2(pv[2], pv[3]);
         u.z = pack_bf16x2(pv[4], pv[5]);
         u.w = pack_bf16x2(pv[6], pv[7]);
-        uint8_t* dst = sPt + (ch >> 3) * kBoxBytes + row * 128 + (((ch & 7) ^ (row & 7)) << 4);
-        *reinterpret_cast<uint4*>(dst) = u;
+        sts128(sp_row + (ch >> 3) * kBoxBytes + (((ch & 7) ^ (row & 7)) << 4), u.x, u.y, u.z, u.w);
       }
-      l_run = l_run * alpha + rs;
+      l_run = l_run * alpha + ((rs4[0] + rs4[1]) + (rs4[2] + rs4[3]));
       fence_proxy_async();
       mbar_arrive(&p_full[t]);
       if (j > 0) {
