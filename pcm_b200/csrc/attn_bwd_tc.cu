@@ -13,6 +13,7 @@
 // warpgroups (8 warps, two per SM sub-partition): warpgroup g handles score columns [64g, 64g+64).
 // Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warps 4-11 element-wise + epilogue.
 #include <stdlib.h>
+#include <type_traits>
 #include "common.cuh"
 #include "host_common.h"
 #include "../../include/pcm_b200.h"
@@ -38,13 +39,10 @@ __device__ __forceinline__ float fexp2(float x) {
 }
 
 // write 8 bf16 (one 16-byte chunk `ch` of row `row`) into a K-major SWIZZLE_128B operand tile pair
-__device__ __forceinline__ void st_operand_chunk(uint8_t* base, int row, int ch, const float (&v)[8]) {
-  uint4 u;
-  u.x = pack_bf16x2(v[0], v[1]);
-  u.y = pack_bf16x2(v[2], v[3]);
-  u.z = pack_bf16x2(v[4], v[5]);
-  u.w = pack_bf16x2(v[6], v[7]);
-  *reinterpret_cast<uint4*>(base + (ch >> 3) * kBoxB + row * 128 + (((ch & 7) ^ (row & 7)) << 4)) = u;
+// (base = shared-space address of the tile pair)
+__device__ __forceinline__ void st_operand_chunk(uint32_t base, int row, int ch, const float (&v)[8]) {
+  sts128(base + (ch >> 3) * kBoxB + row * 128 + (((ch & 7) ^ (row & 7)) << 4), pack_bf16x2(v[0], v[1]),
+         pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -192,14 +190,25 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_dkdv_tc_kernel(const 
       }
       mbar_arrive(&kv_ready);
     }
+    const uint32_t sP_u = smem_u32(sP), sdS_u = smem_u32(sdS);
+    const uint32_t sL_u = smem_u32(sL), sD_u = smem_u32(sD);
+    // per-query statistics (first 128 threads stage them): fetched one tile ahead so that the HBM
+    // latency never sits between two tiles; L = +inf past the end
+    float l_pre = INFINITY, d_pre = 0.f;
+    if (et < 128 && et < p.Sq) {
+      l_pre = Lg[et];
+      d_pre = Dg[et];
+    }
     for (int j = 0; j < ntiles; ++j) {
       const int st = j % ST;
-      // stage the per-query statistics of this tile (first 128 threads), L = +inf past the end
       if (et < 128) {
-        const int qi = j * 128 + et;
-        sL[st * 128 + et] = qi < p.Sq ? Lg[qi] : INFINITY;
-        sD[st * 128 + et] = qi < p.Sq ? Dg[qi] : 0.f;
+        sL[st * 128 + et] = l_pre;
+        sD[st * 128 + et] = d_pre;
         mbar_arrive(&ld_full[st]);
+        const int qn = (j + 1) * 128 + et;
+        const bool vn = j + 1 < ntiles && qn < p.Sq;
+        l_pre = vn ? Lg[qn] : INFINITY;
+        d_pre = vn ? Dg[qn] : 0.f;
       }
       mbar_wait(&ld_full[st], (j / ST) & 1);
       mbar_wait(&s_full, j & 1);
@@ -222,15 +231,20 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_dkdv_tc_kernel(const 
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
           float pv[8], gv[8];
+          // the 8 queries' statistics: two broadcast 16-byte shared loads each
+          const uint32_t so = (st * 128 + col0 + ch * 8) * 4;
+          const float4 l0 = lds128(sL_u + so), l1 = lds128(sL_u + so + 16);
+          const float4 d0 = lds128(sD_u + so), d1 = lds128(sD_u + so + 16);
+          const float lq[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+          const float dq8[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
-            const int q = col0 + ch * 8 + e;
-            const float pe = kvalid ? fexp2(fmaf(__uint_as_float(sv[cc][ch * 8 + e]), c, -sL[st * 128 + q])) : 0.f;
+            const float pe = kvalid ? fexp2(fmaf(__uint_as_float(sv[cc][ch * 8 + e]), c, -lq[e])) : 0.f;
             pv[e] = pe;
-            gv[e] = pe * (__uint_as_float(dv[cc][ch * 8 + e]) - sD[st * 128 + q]);
+            gv[e] = pe * (__uint_as_float(dv[cc][ch * 8 + e]) - dq8[e]);
           }
-          st_operand_chunk(sP, row, (col0 >> 3) + ch, pv);
-          st_operand_chunk(sdS, row, (col0 >> 3) + ch, gv);
+          st_operand_chunk(sP_u, row, (col0 >> 3) + ch, pv);
+          st_operand_chunk(sdS_u, row, (col0 >> 3) + ch, gv);
         }
       }
       fence_proxy_async();
@@ -289,9 +303,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_dq_tc_kernel(const __
   uint8_t* sdO = sQ + kBoxB;
   uint8_t* sK = sdO + kBoxB;          // [ST]
   uint8_t* sV = sK + ST * kBoxB;      // [ST]
-  uint8_t* sdS = sV + ST * kBoxB;     // 2 boxes
-  __shared__ __align__(8) uint64_t q_full, q_ready, kv_full[ST], kv_free[ST], s_full, s_free, p_full, p_free,
-      acc_full;
+  uint8_t* sdS = sV + ST * kBoxB;     // [2 buffers][2 boxes]: tile j + 1's dS is written while
+                                      // the dQ MMAs of tile j still read theirs
+  __shared__ __align__(8) uint64_t q_full, q_ready, kv_full[ST], kv_free[ST], s_full, s_free, p_full[2],
+      p_free[2], acc_full;
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -311,8 +326,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_dq_tc_kernel(const __
     }
     mbar_init(&s_full, 1);
     mbar_init(&s_free, 256);
-    mbar_init(&p_full, 256);
-    mbar_init(&p_free, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&p_full[i], 256);
+      mbar_init(&p_free[i], 1);
+    }
     mbar_init(&acc_full, 1);
     fence_barrier_init();
   }
@@ -367,14 +384,15 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_dq_tc_kernel(const __
         const int st = j % ST;
         if (j + 1 < ntiles) issue_scores(j + 1);
         const uint32_t k_addr = smem_u32(sK + st * kBoxB);
-        mbar_wait(&p_full, j & 1);
+        mbar_wait(&p_full[j & 1], (j >> 1) & 1);
         tc_fence_after();
+        const uint32_t ds_j = ds_addr + (j & 1) * 2 * kBoxB;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {  // 16 keys per step
-          umma_f16(tmem_base + 256, umma_desc_sw128(ds_addr + (k >> 2) * kBoxB + (k & 3) * 32, 16, 1024),
+          umma_f16(tmem_base + 256, umma_desc_sw128(ds_j + (k >> 2) * kBoxB + (k & 3) * 32, 16, 1024),
                    umma_desc_sw128(k_addr + k * 2048, kBoxB, 1024), idesc_g, (j | k) != 0 ? 1u : 0u);
         }
-        umma_commit(&p_free);
+        umma_commit(&p_free[j & 1]);
         umma_commit(&kv_free[st]);
       }
       umma_commit(&acc_full);
@@ -405,6 +423,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_dq_tc_kernel(const __
       }
       mbar_arrive(&q_ready);
     }
+    const uint32_t sdS_u = smem_u32(sdS);
     for (int j = 0; j < ntiles; ++j) {
       mbar_wait(&s_full, j & 1);
       tc_fence_after();
@@ -417,24 +436,31 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_dq_tc_kernel(const __
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(&s_free);
-      if (j > 0) mbar_wait(&p_free, (j - 1) & 1);
+      if (j >= 2) mbar_wait(&p_free[j & 1], ((j >> 1) - 1) & 1);  // dQ MMAs of tile j - 2 done
+      const uint32_t ds_u = sdS_u + (j & 1) * 2 * kBoxB;
+      auto tile_math = [&](auto masked) {
 #pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        const int col0 = g * 64 + cc * 32;
+        for (int cc = 0; cc < 2; ++cc) {
+          const int col0 = g * 64 + cc * 32;
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          float gv[8];
+          for (int ch = 0; ch < 4; ++ch) {
+            float gv[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int key = j * 128 + col0 + ch * 8 + e;
-            const float pe = key < p.Skv ? fexp2(fmaf(__uint_as_float(sv[cc][ch * 8 + e]), c, -lrow)) : 0.f;
-            gv[e] = pe * (__uint_as_float(dv[cc][ch * 8 + e]) - drow);
+            for (int e = 0; e < 8; ++e) {
+              float pe = fexp2(fmaf(__uint_as_float(sv[cc][ch * 8 + e]), c, -lrow));
+              if constexpr (decltype(masked)::value) {
+                if (j * 128 + col0 + ch * 8 + e >= p.Skv) pe = 0.f;
+              }
+              gv[e] = pe * (__uint_as_float(dv[cc][ch * 8 + e]) - drow);
+            }
+            st_operand_chunk(ds_u, row, (col0 >> 3) + ch, gv);
           }
-          st_operand_chunk(sdS, row, (col0 >> 3) + ch, gv);
         }
-      }
+      };
+      if ((j + 1) * 128 <= p.Skv) tile_math(std::false_type{});
+      else tile_math(std::true_type{});
       fence_proxy_async();
-      mbar_arrive(&p_full);
+      mbar_arrive(&p_full[j & 1]);
     }
     // epilogue: warpgroup g writes dQ columns [g * DP/2 ...) -- split by 16-column TMEM chunks
     mbar_wait(&acc_full, 0);
@@ -484,7 +510,7 @@ static int enc_map(CUtensorMap* map, const void* ptr, int C, int S, int B, long 
 template <int DP>
 static int launch_bwd_tc(const AttnBwdTcParams& p, cudaStream_t stream) {
   const size_t smem1 = static_cast<size_t>(2 + 2 * 2 + 4) * kBoxB + 4 * 128 * sizeof(float) + 1024;
-  const size_t smem2 = static_cast<size_t>(2 + 2 * 3 + 2) * kBoxB + 1024;
+  const size_t smem2 = static_cast<size_t>(2 + 2 * 3 + 4) * kBoxB + 1024;  // dS double-buffered
   static bool set = false;
   if (!set) {
     CUDA_TRY(cudaFuncSetAttribute(attn_bwd_dkdv_tc_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
