@@ -146,6 +146,9 @@ def usable_cores():
     return best
 
 
+_CPU_NET = {}
+
+
 def cpu_forward_sample(hw=64, repeats=1, threads=None):
     """Bounded CPU sample of the workload: ONE LoRA-student UNet forward of ONE sample through the
     restated reference (oracle, fp32, all host threads).  Returns (seconds, cores)."""
@@ -153,9 +156,10 @@ def cpu_forward_sample(hw=64, repeats=1, threads=None):
     cores = threads or usable_cores()
     torch.set_num_threads(cores)
     cfg = unet_ref.SD15
-    P = unet_ref.init_params(cfg, 0)
-    batch = pcm_ref.make_batch(cfg, 1, hw, seed=0)
-    net = unet_ref.UNetRef(cfg, P, use_lora=True)
+    if hw not in _CPU_NET:   # weights are built once per process, not per timed sample
+        P = unet_ref.init_params(cfg, 0)
+        _CPU_NET[hw] = (unet_ref.UNetRef(cfg, P, use_lora=True), pcm_ref.make_batch(cfg, 1, hw, seed=0))
+    net, batch = _CPU_NET[hw]
     ts = torch.tensor([499])
     best = None
     with torch.no_grad():
@@ -184,7 +188,7 @@ def run_reference(args, rank, world):
     per = []
     cores = usable_cores()
     for i in range(args.warmup + args.steps):
-        t, cores = cpu_forward_sample(hw)
+        t, cores = cpu_forward_sample(hw, threads=cores)
         if i >= args.warmup:
             per.append(t)
     t_fwd = sum(per) / len(per)
