@@ -142,7 +142,10 @@ def gemm(a_srcs, b_srcs, prog, *, lin, M, N, out, geo=(1, 1), bias=None, rowvec=
     LAUNCHES["count"] += 1
     if DRY_RUN is not None:
         DRY_RUN.append(("gemm", dict(M=M, N=N, K=64 * sum(e[4] for e in prog), bn=d.block_n, lin=int(lin),
-                                     nprog=len(prog), res=residual is not None, ksplit=d.ksplit)))
+                                     nprog=len(prog), res=residual is not None, ksplit=d.ksplit,
+                                     prog=[tuple(e) for e in prog], num_a=len(a_srcs), num_b=len(b_srcs),
+                                     a_C=[a.C for a in a_srcs], b_K=[b.K for b in b_srcs],
+                                     b_N=[b.N for b in b_srcs])))
         return out
     if PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

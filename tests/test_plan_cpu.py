@@ -1,0 +1,107 @@
+"""Host-side launch-plan checks that need no GPU: the step is sequenced in DRY_RUN mode (ops record
+instead of launching) and the recorded K programs / operand layouts are validated against the rules
+the CUDA side enforces (pcm_gemm: gemm_tc.cu launch_gemm) - so a plan bug fails here, on CPU."""
+import collections
+
+import pytest
+import torch
+
+
+@pytest.fixture(scope="module")
+def dry_step():
+    from pcm_b200 import config, ops, weights
+    from pcm_b200.step import PCMTrainStep
+    old = ops.DRY_RUN
+    ops.DRY_RUN = []
+    try:
+        cfg = config.TINY
+        sd = weights.synthetic_state_dict(cfg, 0)
+        st = PCMTrainStep(cfg, sd, "cpu", batch=2, height=16, width=16, multiphase=4)
+        ops.DRY_RUN.clear()
+        st.run_eager()
+        rec = list(ops.DRY_RUN)
+    finally:
+        ops.DRY_RUN = old
+    return st, rec
+
+
+def test_k_programs_are_valid(dry_step):
+    from pcm_b200 import _lib
+    _, rec = dry_step
+    gemms = [r[1] for r in rec if r[0] == "gemm"]
+    assert gemms
+    ranged = 0
+    for g in gemms:
+        assert 1 <= g["num_a"] <= _lib.MAX_ASRC and 1 <= g["num_b"] <= _lib.MAX_BSRC
+        assert 1 <= len(g["prog"]) <= _lib.MAX_PROG
+        bn = g["bn"]
+        assert 32 <= bn <= 256 and bn % 32 == 0
+        has_range = False
+        for e in g["prog"]:
+            a_src, b_src, dw, dh, nch, a_c0, b_k0 = e[:7]
+            assert 0 <= a_src < g["num_a"] and 0 <= b_src < g["num_b"] and nch >= 1
+            assert a_c0 % 64 == 0 and b_k0 % 64 == 0
+            assert a_c0 + 64 * nch <= g["a_C"][a_src] + 63, (e, g["a_C"])      # within the A channels
+            assert b_k0 + 64 * nch <= g["b_K"][b_src], (e, g["b_K"])            # within the B rows' K
+            assert g["b_N"][b_src] >= min(g["N"], g["b_N"][b_src])
+            if len(e) > 7 and e[8]:
+                n_lo, n_hi = e[7], e[8]
+                has_range = True
+                assert n_lo % bn == 0 and n_lo < n_hi <= g["N"]
+                assert n_hi % bn == 0 or n_hi == g["N"]
+        if has_range:
+            ranged += 1
+            assert g["ksplit"] == 1      # N-ranged programs are not split over K
+    assert ranged > 0                    # the q/k/v and cross-attention k/v groups use them
+
+
+def test_grouped_layers_replace_single_launches(dry_step):
+    st, rec = dry_step
+    net = st.net if hasattr(st, "net") else st.unet
+    assert net.groups
+    for lead, G in net.groups.items():
+        assert G.g in (2, 3)
+        assert G.w_stack.shape == (G.g * G.cout, G.cin)
+        for i, L in enumerate(G.layers):
+            # member weights are views into the stacked operand
+            assert L.w_fwd.data_ptr() == G.w_stack[i * G.cout:].data_ptr()
+        if G.lora:
+            r = net.r
+            assert G.a_stack.shape == (G.g * r, G.cin)
+            assert G.sb_stack.shape == (G.g * G.cout, r)
+            assert G.sbt_stack.shape == (G.g * r, G.cout)
+
+
+def test_lora_operand_layout_is_a_partition(dry_step):
+    """Every (A, s*B, (s*B)^T, A^T) copy occupies its own slice of lora_opnd; together they tile it."""
+    st, _ = dry_step
+    net = st.net if hasattr(st, "net") else st.unet
+    spans = []
+    for L in net.lora_layers:
+        lo = L.lora
+        taps = L.k * L.k if L.kind == "conv" else 1
+        na, nb = net.r * taps * L.cin, L.cout * net.r
+        spans += [(lo.o_a_fwd, na), (lo.o_sb_fwd, nb), (lo.o_sb_t, nb), (lo.o_a_t, na)]
+    spans.sort()
+    pos = 0
+    for off, n in spans:
+        assert off == pos, (off, pos)
+        pos += n
+    assert pos == net.lora_opnd.numel()
+    # the refresh table addresses exactly these slices
+    tab = net.refresh_table.cpu()
+    assert tab.shape[0] == len(net.lora_layers)
+    for row, L in zip(tab.tolist(), net.lora_layers):
+        lo = L.lora
+        assert row[2:6] == [lo.o_a_fwd, lo.o_sb_fwd, lo.o_sb_t, lo.o_a_t]
+
+
+def test_launch_census(dry_step):
+    _, rec = dry_step
+    c = collections.Counter(r[0] for r in rec)
+    # one pass each of the PCM math kernels, one optimiser, one LoRA refresh
+    for k in ("pcm_prepare", "pcm_teacher_step", "pcm_loss", "pcm_grad_sumsq", "pcm_adamw_clip", "pcm_lora_refresh"):
+        assert c[k] == 1, (k, c[k])
+    assert c["pcm_add_noise"] == 3
+    assert c["gemm"] > c["wgrad"] > 0
+    assert c["pcm_attn_bwd"] * 2 == c["pcm_attn_fwd"]      # merged student+teacher pass + target pass
