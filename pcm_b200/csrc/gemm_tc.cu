@@ -1,7 +1,7 @@
 // tcgen05 / TMEM / TMA implicit-GEMM for sm_100a.
 //
 //   pcm_gemm  : out[M, N] = alpha * sum_k A[m, k] * Bw[n, k]  (+bias, +per-image row vector,
-//               +residual, optional SiLU).  A is gathered by TMA from up to 4 NHWC bf16 tensors
+//               +residual, optional SiLU).  A is gathered by TMA from up to 6 NHWC bf16 tensors
 //               through a "K program" (spatial taps x channel chunks x K segments), so the same
 //               kernel runs nn.Linear, 1x1 / 3x3 / stride-2 convolutions (parity planes),
 //               skip-concat convolutions (two K segments), the LoRA up-projection fused as an
@@ -12,7 +12,8 @@
 // Replaces the cuDNN / cuBLAS calls that diffusers' UNet2DConditionModel + peft LoRA issue for
 // train_pcm_lora_sd15.py:1192-1198, 1219-1223, 1238-1244, 1263-1268 (forwards) and :1296
 // (backward).  Warp roles: warp0 = TMA producer, warp1 = MMA issuer (+TMEM alloc),
-// warps2-5 = epilogue (TMEM -> registers -> global).
+// warps 2-9 = two epilogue groups (TMEM -> registers -> smem transposition -> global).  K-program
+// entries may be restricted to an output-column range (grouped Linear layers sharing their input).
 #include "common.cuh"
 #include "host_common.h"
 #include "../../include/pcm_b200.h"
