@@ -13,7 +13,7 @@ phase with that parity has completed - and returns IMMEDIATELY for parity 1 on a
 tcgen05.commit is an arrival that happens some time after the MMAs issued before it complete (the
 tensor pipe executes MMAs in order).
 
-Usage: python tools/mbar_sim.py [variant ...]   variants: fwd_v2 fwd_lazy_bad fwd_lazy fwd_pbuf2 dq dkdv dkdv_pbuf2_bad dkdv_pbuf2
+Usage: python tools/mbar_sim.py [variant ...]   variants: fwd_v2 fwd_lazy_bad fwd_lazy fwd_pbuf2 fwd_pbuf2_badfinal dq dkdv dkdv_pbuf2_bad dkdv_pbuf2
 (fwd_v2, dq, dkdv = the shipped kernels; *_bad = known-broken protocols kept as self-tests of the model)
 """
 import random
@@ -119,7 +119,7 @@ class Sim:
 # ---------------------------------------------------------------------------------------------
 # forward attention v2 (attn_tc.cu attn_fwd_tc2_kernel): variants of the softmax / MMA protocol
 # ---------------------------------------------------------------------------------------------
-def fwd(sim, ntiles, variant, stages):
+def fwd(sim, ntiles, variant, stages, badfinal=False):
     T = 2
     kv_full = [Bar(f"kv_full{i}", 1) for i in range(stages)]
     kv_free = [Bar(f"kv_free{i}", 1) for i in range(stages)]
@@ -164,7 +164,13 @@ def fwd(sim, ntiles, variant, stages):
                         bb = 0
                         yield ('wait', p_full[t][0], jj & 1)
                         yield ('wait', o_free[t][0], (jj & 1) ^ 1)
-                    yield ('mma', [(f"P{t}{bb}", jj), (f"V{stv}", jj)], [])
+                    if variant in ("lazy", "lazy_bad", "pbuf2"):
+                        # O accumulates in TMEM: block jj adds to the sum of blocks < jj, which the
+                        # softmax warpgroup may have rescaled in place just before
+                        o_in = [] if jj == 0 else [(f"O{t}", ('r', jj) if rescale(jj) else jj - 1)]
+                        yield ('mma', [(f"P{t}{bb}", jj), (f"V{stv}", jj)] + o_in, [(f"O{t}", jj)])
+                    else:
+                        yield ('mma', [(f"P{t}{bb}", jj), (f"V{stv}", jj)], [])
                     yield ('commit', [o_full[t], p_free[t][bb]])
                 yield ('commit', [kv_free[stv]])
                 stv = (stv + 1) % stages
@@ -190,6 +196,8 @@ def fwd(sim, ntiles, variant, stages):
                 if j > 0:
                     if rescale(j):
                         yield ('wait', o_full[t], (j - 1) & 1)
+                        yield ('read', f"O{t}", j - 1)
+                        yield ('write', f"O{t}", ('r', j))
                     yield ('arrive', o_free[t][0])
                     yield ('wait', p_free[t][0], (j - 1) & 1)
                 yield ('write', f"P{t}0", j)
@@ -199,6 +207,8 @@ def fwd(sim, ntiles, variant, stages):
                     yield ('wait', p_free[t][0], (j - 1) & 1)
                     if rescale(j):
                         yield ('wait', o_full[t], (j - 1) & 1)
+                        yield ('read', f"O{t}", j - 1)
+                        yield ('write', f"O{t}", ('r', j))
                     yield ('arrive', o_free[t][0])
                 yield ('write', f"P{t}0", j)
                 yield ('arrive', p_full[t][0])
@@ -209,13 +219,19 @@ def fwd(sim, ntiles, variant, stages):
                 if j > 0:
                     if rescale(j):
                         yield ('wait', o_full[t], (j - 1) & 1)
+                        yield ('read', f"O{t}", j - 1)
+                        yield ('write', f"O{t}", ('r', j))
                     yield ('arrive', o_free[t][bb])
                 yield ('write', f"P{t}{bb}", j)
                 yield ('arrive', p_full[t][bb])
-        if variant == "pbuf2":
+        if variant == "pbuf2" and badfinal and ntiles >= 2:
+            yield ('wait', o_full[t], (ntiles - 2) & 1)   # aliases when o_full is already 2 phases on
+        elif variant == "pbuf2":
             if ntiles >= 2:
                 yield ('wait', p_free[t][(ntiles - 2) & 1], ((ntiles - 2) >> 1) & 1)
         yield ('wait', o_full[t], (ntiles - 1) & 1)
+        if variant in ("lazy", "lazy_bad", "pbuf2"):
+            yield ('read', f"O{t}", ntiles - 1)   # final read-out of the accumulated O
 
     sim.add("producer", producer())
     sim.add("mma", mma())
@@ -369,6 +385,7 @@ VARIANTS = {
     "fwd_lazy_bad": lambda s, n: fwd(s, n, "lazy_bad", 3),
     "fwd_lazy": lambda s, n: fwd(s, n, "lazy", 3),
     "fwd_pbuf2": lambda s, n: fwd(s, n, "pbuf2", 2),
+    "fwd_pbuf2_badfinal": lambda s, n: fwd(s, n, "pbuf2", 2, badfinal=True),
     "dq": lambda s, n: dq(s, n),
     "dkdv": lambda s, n: dkdv(s, n, "single"),
     "dkdv_pbuf2_bad": lambda s, n: dkdv(s, n, "pbuf2_bad"),
