@@ -12,7 +12,7 @@ mbar_sim = importlib.util.module_from_spec(spec)
 spec.loader.exec_module(mbar_sim)
 
 
-@pytest.mark.parametrize("variant", ["fwd_v2", "dq", "dkdv"])
+@pytest.mark.parametrize("variant", ["gemm", "fwd_v2", "dq", "dkdv"])
 def test_shipped_protocols_are_clean(variant):
     assert mbar_sim.check(variant, trials=300) is None
 
@@ -22,7 +22,7 @@ def test_prepared_protocols_are_clean(variant):
     assert mbar_sim.check(variant, trials=300) is None
 
 
-@pytest.mark.parametrize("variant", ["fwd_lazy_bad", "fwd_pbuf2_badfinal", "dkdv_pbuf2_bad"])
+@pytest.mark.parametrize("variant", ["gemm_unpaced_release", "fwd_lazy_bad", "fwd_pbuf2_badfinal", "dkdv_pbuf2_bad"])
 def test_model_catches_known_bugs(variant):
     bad = mbar_sim.check(variant, trials=1500)
     assert bad is not None, "the model no longer finds the known deadlock / race"

@@ -13,7 +13,7 @@ phase with that parity has completed - and returns IMMEDIATELY for parity 1 on a
 tcgen05.commit is an arrival that happens some time after the MMAs issued before it complete (the
 tensor pipe executes MMAs in order).
 
-Usage: python tools/mbar_sim.py [variant ...]   variants: fwd_v2 fwd_lazy_bad fwd_lazy fwd_pbuf2 fwd_pbuf2_badfinal dq dkdv dkdv_pbuf2_bad dkdv_pbuf2
+Usage: python tools/mbar_sim.py [variant ...]   variants: gemm gemm_unpaced_release fwd_v2 fwd_lazy_bad fwd_lazy fwd_pbuf2 fwd_pbuf2_badfinal dq dkdv dkdv_pbuf2_bad dkdv_pbuf2
 (fwd_v2, dq, dkdv = the shipped kernels; *_bad = known-broken protocols kept as self-tests of the model)
 """
 import random
@@ -380,12 +380,69 @@ def dq(sim, ntiles):
         sim.add(f"elem{g}", elem(g))
 
 
+# ---------------------------------------------------------------------------------------------
+# implicit GEMM (gemm_tc.cu): S-stage smem ring, two TMEM accumulators, 8 epilogue warps
+# ---------------------------------------------------------------------------------------------
+def gemm(sim, ntiles, stages=3, kblocks=4, early_release_unpaced=False):
+    full = [Bar(f"full{i}", 1) for i in range(stages)]
+    empty = [Bar(f"empty{i}", 1) for i in range(stages)]
+    tfull = [Bar(f"tfull{i}", 1) for i in range(2)]
+    tempty = [Bar(f"tempty{i}", 8) for i in range(2)]
+
+    def producer():
+        st = ph = 0
+        for t in range(ntiles):
+            for kb in range(kblocks):
+                yield ('wait', empty[st], ph ^ 1)
+                yield ('write', f"stage{st}", (t, kb))
+                yield ('arrive', full[st])
+                st += 1
+                if st == stages:
+                    st, ph = 0, ph ^ 1
+
+    def mma():
+        st = ph = acc = aph = 0
+        for t in range(ntiles):
+            yield ('wait', tempty[acc], aph ^ 1)
+            for kb in range(kblocks):
+                yield ('wait', full[st], ph)
+                yield ('mma', [(f"stage{st}", (t, kb))], [(f"acc{acc}", (t, kb))])
+                yield ('commit', [empty[st]])
+                st += 1
+                if st == stages:
+                    st, ph = 0, ph ^ 1
+            yield ('commit', [tfull[acc]])
+            acc ^= 1
+            if acc == 0:
+                aph ^= 1
+
+    def epi(w):
+        acc = aph = 0
+        idle = (w == 7)   # a warp whose group has no chunk in these tiles (block_n = 32)
+        for t in range(ntiles):
+            if not (idle and early_release_unpaced):
+                yield ('wait', tfull[acc], aph)
+            if not idle:
+                yield ('read', f"acc{acc}", (t, kblocks - 1))
+            yield ('arrive', tempty[acc])
+            acc ^= 1
+            if acc == 0:
+                aph ^= 1
+
+    sim.add("producer", producer())
+    sim.add("mma", mma())
+    for w in range(8):
+        sim.add(f"epi{w}", epi(w))
+
+
 VARIANTS = {
     "fwd_v2": lambda s, n: fwd(s, n, "v2", 3),
     "fwd_lazy_bad": lambda s, n: fwd(s, n, "lazy_bad", 3),
     "fwd_lazy": lambda s, n: fwd(s, n, "lazy", 3),
     "fwd_pbuf2": lambda s, n: fwd(s, n, "pbuf2", 2),
     "fwd_pbuf2_badfinal": lambda s, n: fwd(s, n, "pbuf2", 2, badfinal=True),
+    "gemm": lambda s, n: gemm(s, n),
+    "gemm_unpaced_release": lambda s, n: gemm(s, n, early_release_unpaced=True),
     "dq": lambda s, n: dq(s, n),
     "dkdv": lambda s, n: dkdv(s, n, "single"),
     "dkdv_pbuf2_bad": lambda s, n: dkdv(s, n, "pbuf2_bad"),
