@@ -56,3 +56,21 @@ def test_defaults_actions_types_match(parser_actions):
             if list(a.choices or []) != list(ref["choices"]):
                 bad.append((flag, "choices", a.choices, ref["choices"]))
     assert not bad, bad
+
+
+def test_kohya_export_keys_match_reference():
+    """weights.to_kohya_keys vs the reference's get_module_kohya_state_dict executed verbatim on the
+    same 278 LoRA modules (tests/golden/kohya_keys.json, make_kohya_golden.py)."""
+    import torch
+    from pcm_b200 import weights
+    gold = json.load(open(os.path.join(HERE, "golden", "kohya_keys.json")))
+    lora_sd = {}
+    for m in gold["modules"]:
+        lora_sd[m + ".lora_A.weight"] = torch.zeros(1)
+        lora_sd[m + ".lora_B.weight"] = torch.zeros(1)
+    assert len(gold["modules"]) == 278
+    peft = weights.to_peft_keys(lora_sd)
+    assert all(k.startswith("base_model.model.") for k in peft)
+    out = weights.to_kohya_keys(lora_sd, lora_alpha=8)
+    assert sorted(out.keys()) == gold["kohya_keys"]
+    assert float(next(v for k, v in out.items() if k.endswith(".alpha"))) == gold["alpha"]
