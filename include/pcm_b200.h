@@ -69,7 +69,8 @@ typedef struct {
   float alpha;
   int32_t act;           /* 0 none, 1 SiLU applied to the result */
   int32_t ksplit;        /* > 1: split the K program over ksplit CTAs per tile (small-M, long-K) */
-  void* splitk_ws;       /* fp32 [M, N] scratch for the split-K partial sums (required if ksplit > 1) */
+  void* splitk_ws;       /* fp32 [ksplit, M, N] scratch: one slice of partial sums per K split, added in
+                            split order by the finalize kernel (required if ksplit > 1) */
 } pcm_gemm_desc;
 
 /* LoRA weight-gradient descriptor: out[ch, r] += alpha * sum_m P[m(+tap), ch] * Q[m, r], r < 64.
@@ -84,10 +85,14 @@ typedef struct {
   int32_t num_taps;
   int32_t dw[9], dh[9];
   int64_t tap_off[9];  /* element offset into out per tap */
-  float* out;          /* fp32, accumulated with atomics */
+  float* out;          /* fp32, accumulated (see sem) */
   int64_t os_row, os_col; /* out[tap_off + ch*os_row + r*os_col] */
   int32_t ksplit;      /* token-dimension splits (0 = auto) */
   float alpha;
+  void* sem;           /* NULL: the token splits accumulate with unordered fp32 atomics.  Otherwise
+                          int32[>= ceil(Cp/128) * num_taps], zero-initialised once by the caller: the
+                          splits of one output tile then add in split order (bit-reproducible
+                          gradients); the kernel leaves the semaphores at zero */
 } pcm_wgrad_desc;
 
 const char* pcm_last_error(void);
@@ -102,15 +107,20 @@ int pcm_wgrad(const pcm_wgrad_desc* d, void* stream);
  * Replace ATen group_norm/layer_norm/silu inside diffusers ResnetBlock2D / Transformer2DModel /
  * BasicTransformerBlock (T15:1192-1198, 1219-1244, 1263-1268) and their backward (T15:1296).
  * x2/C2 (may be NULL/0) is the second half of a channel concat (up-block skip connections).
- * stats: [B, G, 2] (sum, sumsq) written by fwd, consumed by bwd; red: [B, G, 2] scratch. */
+ * stats: [B, G, 2] (mean, rstd) written by fwd, consumed by bwd; red: [B, G, 2] scratch.
+ * ws / ws_bytes: caller-owned scratch of at least pcm_groupnorm_ws_bytes(B, HW, C1 + C2, G) bytes,
+ * zero-initialised ONCE (the kernels restore the zeros): per-block partial statistics are merged in
+ * block order, so results are bit-reproducible; variance is computed from pivot-shifted sums and
+ * Chan's formula (no E[x^2] - mean^2 cancellation). */
+int64_t pcm_groupnorm_ws_bytes(int B, int HW, int C, int G);
 int pcm_groupnorm_fwd(const void* x1, const void* x2, int C1, int C2, int B, int HW, int G,
                       const float* gamma, const float* beta, float eps, int silu, void* out,
-                      float* stats, void* stream);
+                      float* stats, void* ws, int64_t ws_bytes, void* stream);
 int pcm_groupnorm_bwd(const void* dy, const void* x1, const void* x2, int C1, int C2, int B, int HW,
                       int G, const float* gamma, const float* beta, float eps, int silu,
                       const float* stats, float* red, const void* add, void* dx1, void* dx2,
                       float* colsum /* optional fp32 [B, C]: per-image column sums of dx */,
-                      void* stream);
+                      void* ws, int64_t ws_bytes, void* stream);
 /* stats: [M, 2] (mean, rstd) */
 int pcm_layernorm_fwd(const void* x, int M, int C, const float* gamma, const float* beta, float eps,
                       void* out, float* stats, void* stream);
@@ -168,6 +178,9 @@ int pcm_axpby_f64(const float* x, const float* y, const double* ca, const double
                   int B, double* out, void* stream);
 
 /* ---- optimiser on the flat fp32 LoRA buffer (T15:1297-1301) ------------------------------- */
+/* out: PCM_SUMSQ_WS_DOUBLES doubles, zero-initialised once: out[0] = sum of squares; the rest is
+ * scratch (block counter + per-block partials added in block order: bit-reproducible norm) */
+#define PCM_SUMSQ_WS_DOUBLES 1024
 int pcm_grad_sumsq(const float* g, int64_t n, double* out, void* stream);
 /* state: device float[2] = {lr, step}; step is incremented on device before the update */
 int pcm_adamw_clip(float* p, float* g, float* m, float* v, int64_t n, float* state, float beta1,

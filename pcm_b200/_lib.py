@@ -10,6 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libpcm_b200.so")
 
 MAX_ASRC, MAX_BSRC, MAX_PROG = 6, 4, 24
+SUMSQ_WS_DOUBLES = 1024   # PCM_SUMSQ_WS_DOUBLES
 
 
 class ASrc(C.Structure):
@@ -45,7 +46,7 @@ class WgradDesc(C.Structure):
         ("geoW", C.c_int32), ("geoH", C.c_int32), ("num_taps", C.c_int32),
         ("dw", C.c_int32 * 9), ("dh", C.c_int32 * 9), ("tap_off", C.c_int64 * 9),
         ("out", C.c_void_p), ("os_row", C.c_int64), ("os_col", C.c_int64),
-        ("ksplit", C.c_int32), ("alpha", C.c_float),
+        ("ksplit", C.c_int32), ("alpha", C.c_float), ("sem", C.c_void_p),
     ]
 
 
@@ -65,7 +66,9 @@ def lib():
         _lib.pcm_last_error.restype = C.c_char_p
         for name in EXPORTS:
             fn = getattr(_lib, name)
-            if name not in ("pcm_last_error",):
+            if name == "pcm_groupnorm_ws_bytes":
+                fn.restype = C.c_int64
+            elif name not in ("pcm_last_error",):
                 fn.restype = C.c_int
             if name in ARGTYPES:
                 fn.argtypes = ARGTYPES[name]
@@ -79,6 +82,7 @@ EXPORTS = [
     "pcm_num_sms",
     "pcm_gemm",
     "pcm_wgrad",
+    "pcm_groupnorm_ws_bytes",
     "pcm_groupnorm_fwd",
     "pcm_groupnorm_bwd",
     "pcm_layernorm_fwd",
@@ -110,8 +114,9 @@ P, I, L64, F = C.c_void_p, C.c_int, C.c_int64, C.c_float
 ARGTYPES = {
     "pcm_gemm": [P, P],
     "pcm_wgrad": [P, P],
-    "pcm_groupnorm_fwd": [P, P, I, I, I, I, I, P, P, F, I, P, P, P],
-    "pcm_groupnorm_bwd": [P, P, P, I, I, I, I, I, P, P, F, I, P, P, P, P, P, P, P],
+    "pcm_groupnorm_ws_bytes": [I, I, I, I],
+    "pcm_groupnorm_fwd": [P, P, I, I, I, I, I, P, P, F, I, P, P, P, L64, P],
+    "pcm_groupnorm_bwd": [P, P, P, I, I, I, I, I, P, P, F, I, P, P, P, P, P, P, P, L64, P],
     "pcm_layernorm_fwd": [P, I, I, P, P, F, P, P, P],
     "pcm_layernorm_bwd": [P, P, I, I, P, P, P, P, P],
     "pcm_attn_fwd": [P, P, P, P, P, I, I, I, I, I, L64, L64, L64, L64, F, P],

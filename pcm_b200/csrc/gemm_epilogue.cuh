@@ -18,21 +18,22 @@ namespace pcm {
 
 // Generic phase 2 of one chunk for the calling thread's 4 rows: ragged N, fp32 output, split-K.
 static __device__ __noinline__ void gemm_epilogue_rows_generic(const GemmParams& p, const float* sb, int tm,
-                                                        int n, int r0, int cg) {
+                                                        int n, int r0, int cg, float* ws) {
 #pragma unroll 1
   for (int i = 0; i < 4; ++i) {
     const int rr = r0 + 32 * i;
     const int m = tm * 128 + rr;
     if (m >= p.M) continue;
     const float* srow = sb + rr * 32;
-    if (p.ws) {  // split-K partial sums (fp32 atomics; the finalize kernel applies the epilogue)
+    if (ws) {  // split-K partial sums: plain stores into this split's slice of the workspace (the
+               // finalize kernel adds the slices in split order and applies the epilogue)
       const float4 a0 = *reinterpret_cast<const float4*>(srow + ((2 * cg) ^ (rr & 7)) * 4);
       const float4 a1 = *reinterpret_cast<const float4*>(srow + ((2 * cg + 1) ^ (rr & 7)) * 4);
       const float f[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-      float* wp = p.ws + static_cast<long long>(m) * p.N + n;
+      float* wp = ws + static_cast<long long>(m) * p.N + n;
 #pragma unroll
       for (int e = 0; e < 8; ++e)
-        if (n + e < p.N) atomicAdd(wp + e, f[e] * p.alpha);
+        if (n + e < p.N) wp[e] = f[e] * p.alpha;
       continue;
     }
     const int b = m / p.epiHW;
@@ -69,7 +70,7 @@ template <class Release>
 __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, int tm, int n0, uint32_t taddr,
                                                    float* sb, int lane, int row, int grp, int cg,
                                                    int r0, uint64_t* tfull, uint32_t tfull_phase,
-                                                   Release release) {
+                                                   Release release, float* ws = nullptr) {
   const bool has_bias = p.bias != nullptr, has_rv = p.rowvec != nullptr;
   // split-K, fp32 output and the SiLU epilogue (time-embedding MLP, M = batch) take the generic path
   const bool fast_ok = p.ws == nullptr && !p.out_fp32 && p.act == 0;
@@ -186,7 +187,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, int tm, 
         load_res(rnext, jj + 2);
       }
     } else if (n < p.N) {
-      gemm_epilogue_rows_generic(p, sb, tm, n, r0, cg);
+      gemm_epilogue_rows_generic(p, sb, tm, n, r0, cg, ws);
     }
     // staging tile consumed: the group may overwrite it in its next chunk
     asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");

@@ -29,8 +29,9 @@ struct alignas(64) GemmParams {
   float alpha;
   int act;
   int filtered;      // some K entries carry an N range (per-tile K-block count varies)
-  int ksplit;        // > 1: work item = (tile, K split); fp32 partial sums are atomically added
-  float* ws;         // into ws[m * N + n]; bias / residual / activation run in the finalize kernel
+  int ksplit;        // > 1: work item = (tile, K split); split s stores its fp32 partial sums to
+  float* ws;         // ws[s][m * N + n]; the finalize kernel adds the slices in order and applies
+                     // bias / residual / activation
 };
 
 constexpr int kATileBytes = 128 * 128;  // 128 rows x 64 bf16

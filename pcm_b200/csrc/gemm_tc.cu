@@ -181,8 +181,10 @@ pcm_gemm_kernel(const __grid_constant__ GemmParams p) {
       const int n0 = tn * p.block_n;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256;
       uint64_t* tempty = &tempty_bar[acc];
+      // split-K: this item's partial sums go to slice (item % ksplit) of the workspace
+      float* ws = p.ws ? p.ws + static_cast<long long>(item - tile * p.ksplit) * p.M * p.N : nullptr;
       gemm_epilogue_tile(p, tm, n0, taddr, sb, lane, row, grp, cg, r0, &tfull_bar[acc], acc_phase,
-                         [tempty]() { mbar_arrive(tempty); });
+                         [tempty]() { mbar_arrive(tempty); }, ws);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -196,7 +198,8 @@ pcm_gemm_kernel(const __grid_constant__ GemmParams p) {
   }
 }
 
-// split-K finalize: out = act(ws + bias + rowvec + residual), same row mapping as the GEMM epilogue
+// split-K finalize: out = act(sum over the ksplit workspace slices, in split order, + bias + rowvec
+// + residual), same row mapping as the GEMM epilogue.  Fixed summation order: reproducible.
 __global__ void splitk_finalize_kernel(const GemmParams p) {
   griddep_sync();
   const int nvec = (p.N + 7) >> 3;
@@ -210,8 +213,11 @@ __global__ void splitk_finalize_kernel(const GemmParams p) {
     const int h = r / p.epiW;
     const int w = r - h * p.epiW;
     const long long o = b * p.osB + h * p.osH + w * p.osW;
+    const long long slice = static_cast<long long>(p.M) * p.N;
     for (int e = 0; e < 8 && n + e < p.N; ++e) {
-      float x = p.ws[static_cast<long long>(m) * p.N + n + e];
+      const float* wp = p.ws + static_cast<long long>(m) * p.N + n + e;
+      float x = wp[0];
+      for (int k = 1; k < p.ksplit; ++k) x += wp[k * slice];
       if (p.bias) x += p.bias[n + e];
       if (p.rowvec) x += __bfloat162float(p.rowvec[b * p.rowvec_ld + n + e]);
       if (p.residual) x += __bfloat162float(p.residual[o + n + e]);
@@ -241,6 +247,7 @@ struct alignas(64) WgradParams {
   float* out;
   long long os_row, os_col;
   float alpha;
+  int* sem;  // deterministic mode: one turnstile per (channel tile, tap); NULL = unordered atomics
 };
 
 constexpr int kWgStages = 4;
@@ -345,6 +352,17 @@ pcm_wgrad_kernel(const __grid_constant__ WgradParams p) {
     tc_fence_after();
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     float* o = p.out + p.tap_off[tap] + static_cast<long long>(ch) * p.os_row;
+    // Deterministic mode: the token splits of one output tile add their partial sums in split
+    // order (turnstile on a per-tile semaphore).  Lower blockIdx.z CTAs are dispatched first and
+    // never wait on higher ones, so the chain cannot deadlock.
+    int* sem = p.sem ? p.sem + (blockIdx.y * gridDim.x + blockIdx.x) : nullptr;
+    if (sem) {
+      if (threadIdx.x == 64) {
+        while (atomicAdd(sem, 0) != static_cast<int>(blockIdx.z)) __nanosleep(64);
+        __threadfence();
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
     for (int j = 0; j < 64; j += 32) {
       uint32_t v[32];
       tmem_ld_32x32(taddr + j, v);
@@ -354,6 +372,12 @@ pcm_wgrad_kernel(const __grid_constant__ WgradParams p) {
         for (int i = 0; i < 32; ++i)
           atomicAdd(o + static_cast<long long>(j + i) * p.os_col, __uint_as_float(v[i]) * p.alpha);
       }
+    }
+    if (sem) {
+      __threadfence();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (threadIdx.x == 64)
+        atomicExch(sem, blockIdx.z + 1 == gridDim.z ? 0 : static_cast<int>(blockIdx.z) + 1);
     }
   }
   tc_fence_before();
@@ -478,7 +502,6 @@ static int launch_gemm(const pcm_gemm_desc* d, cudaStream_t stream) {
     GemmParams q = p;
     q.ws = reinterpret_cast<float*>(d->splitk_ws);
     q.bias = nullptr; q.rowvec = nullptr; q.residual = nullptr; q.act = 0;
-    CUDA_TRY(cudaMemsetAsync(q.ws, 0, sizeof(float) * static_cast<size_t>(p.M) * p.N, stream));
     CUDA_TRY(launch_pdl(pcm_gemm_kernel, dim3(grid), dim3(kGemmThreads), smem, stream, q));
     GemmParams f = p;
     f.ws = q.ws;
@@ -527,7 +550,12 @@ static int launch_wgrad(const pcm_wgrad_desc* d, cudaStream_t stream) {
     if (ks < 1) ks = 1;
   }
   if (ks > p.kblocks_total) ks = p.kblocks_total;
+  {  // every split non-empty (the deterministic turnstile passes through every blockIdx.z)
+    const int per = (p.kblocks_total + ks - 1) / ks;
+    ks = (p.kblocks_total + per - 1) / per;
+  }
   p.ksplit = ks;
+  p.sem = reinterpret_cast<int*>(d->sem);
   p.out = d->out;
   p.os_row = d->os_row;
   p.os_col = d->os_col;

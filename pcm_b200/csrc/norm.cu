@@ -6,6 +6,7 @@
 // Transformer2DModel and BasicTransformerBlock (called from train_pcm_lora_sd15.py:1192-1198,
 // 1219-1244, 1263-1268) and their autograd backward (:1296).  GroupNorm reads an optional second
 // source so the up-block skip concat torch.cat([h, res], dim=1) is never materialised twice.
+#include <stdlib.h>
 #include "common.cuh"
 #include "host_common.h"
 #include "../../include/pcm_b200.h"
@@ -13,26 +14,62 @@
 namespace pcm {
 
 // ------------------------------------------------------------------------------------------
-// GroupNorm statistics: stats[b, g] = (sum, sumsq) over HW x (C/G) elements
+// GroupNorm statistics: stats[b, g] = (mean, rstd) over HW x (C/G) elements.
+//
+// Reproducible and cancellation free (torch / diffusers use a Welford-style computation):
+//   * every block accumulates, per channel, sums of (x - pivot) and (x - pivot)^2 with the pivot =
+//     the channel's value at the first pixel of the image, so |x - pivot| = O(sigma) even when
+//     |mean| >> sigma; the channels of a group are merged with Chan's parallel-variance formula;
+//   * the block writes its (mean, M2) per group to a workspace slot (no atomics on data); the LAST
+//     block of an image to finish (a self-resetting counter) merges the per-block partials in block
+//     order, so the result does not depend on the order in which blocks ran.
 // ------------------------------------------------------------------------------------------
 constexpr int kGnMaxC = 2560;
 constexpr int kGnStage = 4096;   // ny * C <= 4096 floats of per-thread partials (see gn_launch_cfg)
+constexpr int kGnMaxB = 1024;    // counters per kernel family in the workspace
 
 __device__ __forceinline__ const bf16* gn_src(const bf16* x1, const bf16* x2, int C1, int C2,
                                               long long pix, int c) {
   return c < C1 ? x1 + pix * C1 + c : x2 + pix * C2 + (c - C1);
 }
 
+// true for exactly one block per image: the last one to arrive; makes the other blocks' global
+// writes visible to it
+__device__ __forceinline__ bool gn_last_block(unsigned* counter, unsigned nblk) {
+  __shared__ unsigned s_old;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_old = atomicAdd(counter, 1u);
+  __syncthreads();
+  const bool last = s_old == nblk - 1;
+  if (last) __threadfence();
+  return last;
+}
+
+// Chan et al. pairwise update of (count, mean, M2) with a second partial (nb may be 0)
+__device__ __forceinline__ void chan_merge(float& na, float& mean, float& m2, float nb, float mb,
+                                           float m2b) {
+  const float nn = na + nb;
+  if (nn <= 0.f) return;
+  const float d = mb - mean;
+  const float f = nb / nn;
+  mean += d * f;
+  m2 += m2b + d * d * na * f;
+  na = nn;
+}
+
 __global__ void gn_stats_kernel(const bf16* __restrict__ x1, const bf16* __restrict__ x2, int C1,
-                                int C2, int HW, int G, int pix_per_block,
+                                int C2, int HW, int G, int pix_per_block, float eps,
+                                float* __restrict__ part, unsigned* __restrict__ counters,
                                 float* __restrict__ stats) {
   griddep_sync();
-  // per-thread partials are staged as [ty][channel] (plain stores) and tree-summed: shared-memory
-  // atomics cost ~2 cycles per lane and dominated this kernel
+  // per-thread partials are staged as [ty][channel] (plain stores) and summed in a fixed order
   __shared__ float s_sum[kGnStage];
   __shared__ float s_sq[kGnStage];
+  __shared__ float s_piv[kGnMaxC];
   const int C = C1 + C2;
   const int b = blockIdx.y;
+  const int nblk = gridDim.x;
   const int nvec = C >> 3;
   const int tx = threadIdx.x % nvec, ty = threadIdx.x / nvec;
   const int ny = blockDim.x / nvec;
@@ -43,25 +80,41 @@ __global__ void gn_stats_kernel(const bf16* __restrict__ x1, const bf16* __restr
   for (int i = 0; i < 8; ++i) a[i] = q[i] = 0.f;
   if (ty < ny) {
     const int c = tx * 8;
+    float piv[8];
+    {
+      const uint4 u = *reinterpret_cast<const uint4*>(
+          gn_src(x1, x2, C1, C2, static_cast<long long>(b) * HW, c));
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = unpack_bf16x2(w[i]);
+        piv[2 * i] = f.x;
+        piv[2 * i + 1] = f.y;
+      }
+    }
     // four independent 16-byte loads in flight per thread
     for (int p = p0 + ty; p < p1; p += 4 * ny) {
       uint4 u[4];
+      bool ok[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int pp = p + k * ny;
+        ok[k] = pp < p1;
         u[k] = make_uint4(0, 0, 0, 0);
-        if (pp < p1)
+        if (ok[k])
           u[k] = *reinterpret_cast<const uint4*>(
               gn_src(x1, x2, C1, C2, static_cast<long long>(b) * HW + pp, c));
       }
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
+        if (!ok[k]) continue;
         const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const float2 f = unpack_bf16x2(w[i]);
-          a[2 * i] += f.x; q[2 * i] += f.x * f.x;
-          a[2 * i + 1] += f.y; q[2 * i + 1] += f.y * f.y;
+          const float d0 = f.x - piv[2 * i], d1 = f.y - piv[2 * i + 1];
+          a[2 * i] += d0; q[2 * i] += d0 * d0;
+          a[2 * i + 1] += d1; q[2 * i + 1] += d1 * d1;
         }
       }
     }
@@ -69,6 +122,10 @@ __global__ void gn_stats_kernel(const bf16* __restrict__ x1, const bf16* __restr
     *reinterpret_cast<float4*>(&s_sum[ty * C + c + 4]) = make_float4(a[4], a[5], a[6], a[7]);
     *reinterpret_cast<float4*>(&s_sq[ty * C + c]) = make_float4(q[0], q[1], q[2], q[3]);
     *reinterpret_cast<float4*>(&s_sq[ty * C + c + 4]) = make_float4(q[4], q[5], q[6], q[7]);
+    if (ty == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s_piv[c + i] = piv[i];
+    }
   }
   __syncthreads();
   for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
@@ -82,24 +139,72 @@ __global__ void gn_stats_kernel(const bf16* __restrict__ x1, const bf16* __restr
   }
   __syncthreads();
   const int cpg = C / G;
+  const float n = static_cast<float>(p1 - p0);   // pixels per channel in this block
   for (int g = threadIdx.x; g < G; g += blockDim.x) {
-    float s = 0.f, ss = 0.f;
+    float msum = 0.f, m2 = 0.f;
     for (int i = 0; i < cpg; ++i) {
-      s += s_sum[g * cpg + i];
-      ss += s_sq[g * cpg + i];
+      const int ch = g * cpg + i;
+      const float s = s_sum[ch];
+      msum += s_piv[ch] + s / n;
+      m2 += s_sq[ch] - s * s / n;
     }
-    atomicAdd(&stats[(b * G + g) * 2], s);
-    atomicAdd(&stats[(b * G + g) * 2 + 1], ss);
+    const float mg = msum / cpg;
+    float dev = 0.f;
+    for (int i = 0; i < cpg; ++i) {
+      const int ch = g * cpg + i;
+      const float d = s_piv[ch] + s_sum[ch] / n - mg;
+      dev += d * d;
+    }
+    float* o = part + (static_cast<long long>(b * nblk + blockIdx.x) * G + g) * 2;
+    o[0] = mg;
+    o[1] = m2 + n * dev;
   }
+  if (!gn_last_block(&counters[b], nblk)) return;
+  // merge the per-block partials: staged in shared memory by all threads (one round of loads),
+  // then 8 lanes per group fold blocks lane, lane + 8, ... in order and combine in a fixed
+  // shuffle tree - the result is independent of the order in which the blocks ran
+  for (int i = threadIdx.x; i < nblk * G; i += blockDim.x) {
+    const float* o = part + (static_cast<long long>(b) * nblk * G + i) * 2;
+    s_sum[i] = __ldcg(o);
+    s_sq[i] = __ldcg(o + 1);
+  }
+  __syncthreads();
+  if (threadIdx.x < G * 8) {   // whole warps (G * 8 is a multiple of 32 for G = 4 k)
+    const int g = threadIdx.x >> 3, j = threadIdx.x & 7;
+    float na = 0.f, mean = 0.f, m2 = 0.f;
+    for (int k = j; k < nblk; k += 8)
+      chan_merge(na, mean, m2,
+                 static_cast<float>(min(HW, (k + 1) * pix_per_block) - k * pix_per_block) * cpg,
+                 s_sum[k * G + g], s_sq[k * G + g]);
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      const float nb = __shfl_xor_sync(0xffffffffu, na, o);
+      const float mb = __shfl_xor_sync(0xffffffffu, mean, o);
+      const float m2b = __shfl_xor_sync(0xffffffffu, m2, o);
+      // both partners compute the same merge (lower lane's partial first): symmetric result
+      if (j & o) {
+        float ta = nb, tm = mb, t2 = m2b;
+        chan_merge(ta, tm, t2, na, mean, m2);
+        na = ta; mean = tm; m2 = t2;
+      } else {
+        chan_merge(na, mean, m2, nb, mb, m2b);
+      }
+    }
+    if (j == 0) {
+      stats[(b * G + g) * 2] = mean;
+      stats[(b * G + g) * 2 + 1] = rsqrtf(fmaxf(m2 / na, 0.f) + eps);
+    }
+  }
+  if (threadIdx.x == 0) counters[b] = 0;   // ready for the next launch
 }
 
 // out = [silu]( (x - mean) * rstd * gamma + beta ), bf16.  Same thread -> channel-vector mapping as
 // gn_stats_kernel: each thread folds the statistics of its 8 channels into (scale, shift) once and
-// then streams pixels (16-byte load, 8 FMAs, 16-byte store), two pixels in flight.
+// then streams pixels (16-byte load, 8 FMAs, 16-byte store), four pixels in flight.
 __global__ void gn_apply_kernel(const bf16* __restrict__ x1, const bf16* __restrict__ x2, int C1,
                                 int C2, int HW, int G, int pix_per_block,
                                 const float* __restrict__ stats, const float* __restrict__ gamma,
-                                const float* __restrict__ beta, float eps, int silu,
+                                const float* __restrict__ beta, int silu,
                                 bf16* __restrict__ out) {
   griddep_sync();
   const int C = C1 + C2;
@@ -108,15 +213,13 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ x1, const bf16* __restr
   const int tx = threadIdx.x % nvec, ty = threadIdx.x / nvec;
   const int ny = blockDim.x / nvec;
   const int cpg = C / G;
-  const float inv_n = 1.f / (static_cast<float>(HW) * cpg);
   const int c = tx * 8;
   float sc[8], sh[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int g = (c + i) / cpg;
-    const float mean = stats[(b * G + g) * 2] * inv_n;
-    const float var = fmaxf(stats[(b * G + g) * 2 + 1] * inv_n - mean * mean, 0.f);
-    const float rstd = rsqrtf(var + eps);
+    const float mean = stats[(b * G + g) * 2];
+    const float rstd = stats[(b * G + g) * 2 + 1];
     sc[i] = rstd * gamma[c + i];
     sh[i] = beta[c + i] - mean * sc[i];
   }
@@ -159,22 +262,24 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ x1, const bf16* __restr
   }
 }
 
-// backward reductions: red[b, g] = (sum gamma*dyh, sum gamma*dyh*xhat), dyh = dy * silu'(pre)
+// backward reductions: red[b, g] = (sum gamma*dyh, sum gamma*dyh*xhat), dyh = dy * silu'(pre);
+// per-block partials merged in block order by the last block of the image (see gn_stats_kernel)
 __global__ void gn_bwd_stats_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x1,
                                     const bf16* __restrict__ x2, int C1, int C2, int HW, int G,
                                     int pix_per_block, const float* __restrict__ stats,
                                     const float* __restrict__ gamma, const float* __restrict__ beta,
-                                    float eps, int silu, float* __restrict__ red) {
+                                    int silu, float* __restrict__ part,
+                                    unsigned* __restrict__ counters, float* __restrict__ red) {
   griddep_sync();
   __shared__ float s_a[kGnStage];
   __shared__ float s_b[kGnStage];
   const int C = C1 + C2;
   const int b = blockIdx.y;
+  const int nblk = gridDim.x;
   const int nvec = C >> 3;
   const int tx = threadIdx.x % nvec, ty = threadIdx.x / nvec;
   const int ny = blockDim.x / nvec;
   const int cpg = C / G;
-  const float inv_n = 1.f / (static_cast<float>(HW) * cpg);
   const int p0 = blockIdx.x * pix_per_block;
   const int p1 = min(HW, p0 + pix_per_block);
   if (ty < ny) {
@@ -183,9 +288,8 @@ __global__ void gn_bwd_stats_kernel(const bf16* __restrict__ dy, const bf16* __r
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int g = (c + i) / cpg;
-      mean[i] = stats[(b * G + g) * 2] * inv_n;
-      const float var = fmaxf(stats[(b * G + g) * 2 + 1] * inv_n - mean[i] * mean[i], 0.f);
-      rstd[i] = rsqrtf(var + eps);
+      mean[i] = stats[(b * G + g) * 2];
+      rstd[i] = stats[(b * G + g) * 2 + 1];
       gm[i] = gamma[c + i];
       bt[i] = beta[c + i];
       a[i] = q[i] = 0.f;
@@ -235,42 +339,60 @@ __global__ void gn_bwd_stats_kernel(const bf16* __restrict__ dy, const bf16* __r
       s += s_a[g * cpg + i];
       ss += s_b[g * cpg + i];
     }
-    atomicAdd(&red[(b * G + g) * 2], s);
-    atomicAdd(&red[(b * G + g) * 2 + 1], ss);
+    float* o = part + (static_cast<long long>(b * nblk + blockIdx.x) * G + g) * 2;
+    o[0] = s;
+    o[1] = ss;
   }
+  if (!gn_last_block(&counters[b], nblk)) return;
+  __syncthreads();
+  for (int i = threadIdx.x; i < nblk * G; i += blockDim.x) {
+    const float* o = part + (static_cast<long long>(b) * nblk * G + i) * 2;
+    s_a[i] = __ldcg(o);
+    s_b[i] = __ldcg(o + 1);
+  }
+  __syncthreads();
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    float s = 0.f, ss = 0.f;
+    for (int k = 0; k < nblk; ++k) {   // block order: independent of the execution order
+      s += s_a[k * G + g];
+      ss += s_b[k * G + g];
+    }
+    red[(b * G + g) * 2] = s;
+    red[(b * G + g) * 2 + 1] = ss;
+  }
+  if (threadIdx.x == 0) counters[b] = 0;
 }
 
 // dx = rstd * (gamma*dyh - (s1 + xhat*s2)/n) (+ add); written to dx1 (first C1 channels) and
 // dx2 (remaining C2 channels).  Per-thread channel constants hoisted like gn_apply_kernel.
+// colsum (optional): per-image column sums of dx, again as per-block partials merged in block
+// order by the last block of the image.
 __global__ void gn_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x1,
                                     const bf16* __restrict__ x2, int C1, int C2, int HW, int G,
                                     int pix_per_block, const float* __restrict__ stats,
                                     const float* __restrict__ red, const float* __restrict__ gamma,
-                                    const float* __restrict__ beta, float eps, int silu,
+                                    const float* __restrict__ beta, int silu,
                                     const bf16* __restrict__ add, bf16* __restrict__ dx1,
-                                    bf16* __restrict__ dx2, float* __restrict__ colsum) {
+                                    bf16* __restrict__ dx2, float* __restrict__ colsum,
+                                    float* __restrict__ cpart, unsigned* __restrict__ counters) {
   griddep_sync();
-  __shared__ float s_cs[kGnMaxC];
+  __shared__ float s_cs[kGnStage];
   const int C = C1 + C2;
   const int b = blockIdx.y;
+  const int nblk = gridDim.x;
   const int nvec = C >> 3;
   const int tx = threadIdx.x % nvec, ty = threadIdx.x / nvec;
   const int ny = blockDim.x / nvec;
   const int cpg = C / G;
   const float inv_n = 1.f / (static_cast<float>(HW) * cpg);
   const int c = tx * 8;
-  if (colsum) {
-    for (int i = threadIdx.x; i < C; i += blockDim.x) s_cs[i] = 0.f;
-    __syncthreads();
-  }
   float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   float mean[8], rstd[8], gm[8], bt[8], s1[8], s2[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int g = (c + i) / cpg;
-    mean[i] = stats[(b * G + g) * 2] * inv_n;
-    const float var = fmaxf(stats[(b * G + g) * 2 + 1] * inv_n - mean[i] * mean[i], 0.f);
-    rstd[i] = rsqrtf(var + eps);
+    mean[i] = stats[(b * G + g) * 2];
+    rstd[i] = stats[(b * G + g) * 2 + 1];
     gm[i] = gamma[c + i];
     bt[i] = beta[c + i];
     s1[i] = red[(b * G + g) * 2] * inv_n;
@@ -316,12 +438,26 @@ __global__ void gn_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __r
 #pragma unroll
     for (int k = 0; k < 8; ++k) cs[k] += o[k];
   }
-  if (colsum) {  // per-image column sums of dx (time-embedding gradient), fp32
-#pragma unroll
-    for (int k = 0; k < 8; ++k) atomicAdd(&s_cs[c + k], cs[k]);
-    __syncthreads();
-    for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&colsum[b * C + i], s_cs[i]);
+  if (!colsum) return;   // uniform over the grid
+  // per-image column sums of dx (time-embedding gradient), fp32, fixed summation order
+  if (ty < ny) {
+    *reinterpret_cast<float4*>(&s_cs[ty * C + c]) = make_float4(cs[0], cs[1], cs[2], cs[3]);
+    *reinterpret_cast<float4*>(&s_cs[ty * C + c + 4]) = make_float4(cs[4], cs[5], cs[6], cs[7]);
   }
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
+    float s = 0.f;
+    for (int y = 0; y < ny; ++y) s += s_cs[y * C + ch];
+    cpart[static_cast<long long>(b * nblk + blockIdx.x) * C + ch] = s;
+  }
+  if (!gn_last_block(&counters[b], nblk)) return;
+  for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
+    float s = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < nblk; ++k) s += __ldcg(cpart + static_cast<long long>(b * nblk + k) * C + ch);
+    colsum[b * C + ch] = s;
+  }
+  if (threadIdx.x == 0) counters[b] = 0;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -500,6 +636,7 @@ static int gn_launch_cfg(int C, int HW, int B, int* threads, int* ppb, int* nblk
   int target_blocks = (4 * num_sms() + B - 1) / B;
   int p = (HW + target_blocks - 1) / target_blocks;
   if (p < ny * 4) p = ny * 4;
+  if ((HW + p - 1) / p > 128) p = (HW + 127) / 128;   // partials are merged through kGnStage floats
   *ppb = p;
   *nblk = (HW + p - 1) / p;
   return 0;
@@ -509,40 +646,106 @@ static int gn_launch_cfg(int C, int HW, int B, int* threads, int* ppb, int* nblk
 
 using namespace pcm;
 
-extern "C" int pcm_groupnorm_fwd(const void* x1, const void* x2, int C1, int C2, int B, int HW,
+// Workspace layout (caller-owned, zero-initialised ONCE; the kernels leave the counters at zero):
+//   uint32 counters[3][kGnMaxB]  (fwd stats, bwd stats, bwd column sums)
+//   float  partials[...]         per-block partial statistics / column sums
+static inline size_t gn_ws_need(int B, int nblk, int C, int G) {
+  return sizeof(unsigned) * 3 * kGnMaxB +
+         sizeof(float) * static_cast<size_t>(B) * nblk * (2 * G + C);
+}
+
+// Images per launch pair: the second pass over x (apply / bwd apply) should find it in L2, so a
+// pass handles at most PCM_GN_CHUNK_MB (default 24) of input at a time.
+static int gn_chunk_images(int B, long long bytes_per_image) {
+  static long long limit = -1;
+  if (limit < 0) {
+    const char* e = getenv("PCM_GN_CHUNK_MB");
+    limit = (e ? atoll(e) : 24) * 1024 * 1024;
+  }
+  if (limit <= 0) return B;
+  long long n = limit / (bytes_per_image > 0 ? bytes_per_image : 1);
+  if (n < 1) n = 1;
+  return n > B ? B : static_cast<int>(n);
+}
+
+extern "C" int64_t pcm_groupnorm_ws_bytes(int B, int HW, int C, int G) {
+  int threads, ppb, nblk;
+  // the per-chunk launch never uses more blocks per image than a single-image launch would
+  if (gn_launch_cfg(C, HW, 1, &threads, &ppb, &nblk)) return -1;
+  return static_cast<int64_t>(gn_ws_need(B, nblk, C, G));
+}
+
+extern "C" int pcm_groupnorm_fwd(const void* x1_, const void* x2_, int C1, int C2, int B, int HW,
                                  int G, const float* gamma, const float* beta, float eps, int silu,
-                                 void* out, float* stats, void* stream_) {
+                                 void* out_, float* stats, void* ws, int64_t ws_bytes,
+                                 void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   const int C = C1 + C2;
   if (C % G != 0 || C1 % 8 != 0 || C2 % 8 != 0) return set_error("groupnorm: bad channel split");
-  int threads, ppb, nblk;
-  if (int rc = gn_launch_cfg(C, HW, B, &threads, &ppb, &nblk)) return rc;
-  CUDA_TRY(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * B * G, stream));
-  CUDA_TRY(launch_pdl(gn_stats_kernel, dim3(dim3(nblk, B)), dim3(threads), 0, stream, reinterpret_cast<const bf16*>(x1), reinterpret_cast<const bf16*>(x2), C1, C2, HW, G, ppb,
-      stats));
-  CUDA_TRY(launch_pdl(gn_apply_kernel, dim3(dim3(nblk, B)), dim3(threads), 0, stream, reinterpret_cast<const bf16*>(x1), reinterpret_cast<const bf16*>(x2), C1, C2, HW, G, ppb, stats,
-      gamma, beta, eps, silu, reinterpret_cast<bf16*>(out)));
+  if (B > kGnMaxB) return set_error("groupnorm: batch too large for the counter workspace");
+  const bf16* x1 = reinterpret_cast<const bf16*>(x1_);
+  const bf16* x2 = reinterpret_cast<const bf16*>(x2_);
+  bf16* out = reinterpret_cast<bf16*>(out_);
+  unsigned* counters = reinterpret_cast<unsigned*>(ws);
+  float* part = reinterpret_cast<float*>(counters + 3 * kGnMaxB);
+  const int cb = gn_chunk_images(B, 2LL * HW * C);
+  for (int b0 = 0; b0 < B; b0 += cb) {
+    const int nb = B - b0 < cb ? B - b0 : cb;
+    int threads, ppb, nblk;
+    if (int rc = gn_launch_cfg(C, HW, nb, &threads, &ppb, &nblk)) return rc;
+    if (ws == nullptr || static_cast<size_t>(ws_bytes) < gn_ws_need(nb, nblk, C, G))
+      return set_error("groupnorm: workspace too small (see pcm_groupnorm_ws_bytes)");
+    const long long o1 = static_cast<long long>(b0) * HW * C1, o2 = static_cast<long long>(b0) * HW * C2;
+    const bf16* y2 = x2 ? x2 + o2 : nullptr;
+    CUDA_TRY(launch_pdl(gn_stats_kernel, dim3(nblk, nb), dim3(threads), 0, stream, x1 + o1, y2, C1, C2,
+                        HW, G, ppb, eps, part, counters + b0, stats + 2 * b0 * G));
+    CUDA_TRY(launch_pdl(gn_apply_kernel, dim3(nblk, nb), dim3(threads), 0, stream, x1 + o1, y2, C1, C2,
+                        HW, G, ppb, static_cast<const float*>(stats + 2 * b0 * G), gamma, beta, silu,
+                        out + static_cast<long long>(b0) * HW * C));
+  }
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
 
-extern "C" int pcm_groupnorm_bwd(const void* dy, const void* x1, const void* x2, int C1, int C2,
+extern "C" int pcm_groupnorm_bwd(const void* dy_, const void* x1_, const void* x2_, int C1, int C2,
                                  int B, int HW, int G, const float* gamma, const float* beta,
                                  float eps, int silu, const float* stats, float* red,
-                                 const void* add, void* dx1, void* dx2, float* colsum,
-                                 void* stream_) {
+                                 const void* add_, void* dx1_, void* dx2_, float* colsum,
+                                 void* ws, int64_t ws_bytes, void* stream_) {
+  (void)eps;  // folded into stats (mean, rstd) by the forward
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   const int C = C1 + C2;
-  int threads, ppb, nblk;
-  if (int rc = gn_launch_cfg(C, HW, B, &threads, &ppb, &nblk)) return rc;
-  CUDA_TRY(cudaMemsetAsync(red, 0, sizeof(float) * 2 * B * G, stream));
-  if (colsum) CUDA_TRY(cudaMemsetAsync(colsum, 0, sizeof(float) * B * C, stream));
-  CUDA_TRY(launch_pdl(gn_bwd_stats_kernel, dim3(dim3(nblk, B)), dim3(threads), 0, stream, reinterpret_cast<const bf16*>(dy), reinterpret_cast<const bf16*>(x1),
-      reinterpret_cast<const bf16*>(x2), C1, C2, HW, G, ppb, stats, gamma, beta, eps, silu, red));
-  CUDA_TRY(launch_pdl(gn_bwd_apply_kernel, dim3(dim3(nblk, B)), dim3(threads), 0, stream, reinterpret_cast<const bf16*>(dy), reinterpret_cast<const bf16*>(x1),
-      reinterpret_cast<const bf16*>(x2), C1, C2, HW, G, ppb, stats, red, gamma, beta, eps, silu,
-      reinterpret_cast<const bf16*>(add), reinterpret_cast<bf16*>(dx1), reinterpret_cast<bf16*>(dx2),
-      colsum));
+  if (B > kGnMaxB) return set_error("groupnorm: batch too large for the counter workspace");
+  const bf16* dy = reinterpret_cast<const bf16*>(dy_);
+  const bf16* x1 = reinterpret_cast<const bf16*>(x1_);
+  const bf16* x2 = reinterpret_cast<const bf16*>(x2_);
+  const bf16* add = reinterpret_cast<const bf16*>(add_);
+  bf16* dx1 = reinterpret_cast<bf16*>(dx1_);
+  bf16* dx2 = reinterpret_cast<bf16*>(dx2_);
+  unsigned* counters = reinterpret_cast<unsigned*>(ws);
+  float* part = reinterpret_cast<float*>(counters + 3 * kGnMaxB);
+  // dy + x (+ add) are read twice: chunk on their combined footprint
+  const int cb = gn_chunk_images(B, (add ? 6LL : 4LL) * HW * C);
+  for (int b0 = 0; b0 < B; b0 += cb) {
+    const int nb = B - b0 < cb ? B - b0 : cb;
+    int threads, ppb, nblk;
+    if (int rc = gn_launch_cfg(C, HW, nb, &threads, &ppb, &nblk)) return rc;
+    if (ws == nullptr || static_cast<size_t>(ws_bytes) < gn_ws_need(nb, nblk, C, G))
+      return set_error("groupnorm: workspace too small (see pcm_groupnorm_ws_bytes)");
+    const long long o = static_cast<long long>(b0) * HW * C;
+    const long long o1 = static_cast<long long>(b0) * HW * C1, o2 = static_cast<long long>(b0) * HW * C2;
+    const bf16* y2 = x2 ? x2 + o2 : nullptr;
+    float* cpart = part + static_cast<size_t>(nb) * nblk * 2 * G;
+    CUDA_TRY(launch_pdl(gn_bwd_stats_kernel, dim3(nblk, nb), dim3(threads), 0, stream, dy + o, x1 + o1,
+                        y2, C1, C2, HW, G, ppb, stats + 2 * b0 * G, gamma, beta, silu, part,
+                        counters + kGnMaxB + b0, red + 2 * b0 * G));
+    CUDA_TRY(launch_pdl(gn_bwd_apply_kernel, dim3(nblk, nb), dim3(threads), 0, stream, dy + o, x1 + o1,
+                        y2, C1, C2, HW, G, ppb, stats + 2 * b0 * G,
+                        static_cast<const float*>(red + 2 * b0 * G), gamma, beta, silu,
+                        add ? add + o : nullptr, dx1 + o1, dx2 ? dx2 + o2 : nullptr,
+                        colsum ? colsum + static_cast<long long>(b0) * C : nullptr, cpart,
+                        counters + 2 * kGnMaxB + b0));
+  }
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

@@ -13,9 +13,13 @@
 
 namespace pcm {
 
+// out[0] = sum of squares (double).  out[1] is a self-resetting block counter (as uint64), out[2 ..]
+// hold one partial per block: the last block to finish adds them in block order, so the norm - and
+// with it the clip coefficient and the whole update - is bit-reproducible.
 __global__ void sumsq_kernel(const float* __restrict__ g, long long n, double* __restrict__ out) {
   griddep_sync();
   __shared__ double s_part[32];
+  __shared__ unsigned long long s_old;
   double acc = 0.0;
   const long long n4 = n >> 2;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
@@ -31,7 +35,20 @@ __global__ void sumsq_kernel(const float* __restrict__ g, long long n, double* _
   if (threadIdx.x < 32) {
     double v = threadIdx.x < (blockDim.x >> 5) ? s_part[threadIdx.x] : 0.0;
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (threadIdx.x == 0) atomicAdd(out, v);
+    if (threadIdx.x == 0) {
+      out[2 + blockIdx.x] = v;
+      __threadfence();
+      s_old = atomicAdd(reinterpret_cast<unsigned long long*>(out + 1), 1ULL);
+    }
+  }
+  __syncthreads();
+  if (s_old != gridDim.x - 1) return;
+  __threadfence();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (unsigned k = 0; k < gridDim.x; ++k) t += __ldcg(out + 2 + k);
+    out[0] = t;
+    *reinterpret_cast<unsigned long long*>(out + 1) = 0ULL;
   }
 }
 
@@ -157,9 +174,9 @@ using namespace pcm;
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
 
 extern "C" int pcm_grad_sumsq(const float* g, int64_t n, double* out, void* stream) {
-  CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(double), ST(stream)));
   int grid = static_cast<int>((n / 4 + 255) / 256);
-  if (grid > num_sms() * 8) grid = num_sms() * 8;
+  if (grid > num_sms() * 4) grid = num_sms() * 4;
+  if (grid > PCM_SUMSQ_WS_DOUBLES - 2) grid = PCM_SUMSQ_WS_DOUBLES - 2;
   if (grid < 1) grid = 1;
   CUDA_TRY(launch_pdl(sumsq_kernel, dim3(grid), dim3(256), 0, ST(stream), g, n, out));
   CUDA_TRY(cudaGetLastError());

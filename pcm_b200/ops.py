@@ -2,6 +2,7 @@
 across the boundary, work enqueued on torch's current CUDA stream.  No compute happens in Python.
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -44,6 +45,7 @@ LAUNCHES = {"count": 0}
 PROFILE = None  # list of (start_event, end_event, flops) when enabled
 DRY_RUN = None  # list: record (kind, info) instead of launching (shape analysis without a GPU)
 _KERNELS_PER_CALL = {"pcm_groupnorm_fwd": 2, "pcm_groupnorm_bwd": 2, "pcm_attn_bwd": 3, "pcm_adamw_clip": 2}
+
 
 
 def num_sms():
@@ -112,7 +114,8 @@ def gemm(a_srcs, b_srcs, prog, *, lin, M, N, out, geo=(1, 1), bias=None, rowvec=
     d.ksplit = ksplit or 1
     ws = None
     if d.ksplit > 1:
-        ws = torch.empty(M, N, device=out.device, dtype=torch.float32) if DRY_RUN is None else None
+        # one fp32 slice per K split (plain stores, added in split order by the finalize kernel)
+        ws = torch.empty(d.ksplit, M, N, device=out.device, dtype=torch.float32) if DRY_RUN is None else None
         d.splitk_ws = ws.data_ptr() if ws is not None else 0
     d.out = out.data_ptr()
     d.out_fp32 = int(out.dtype == torch.float32)
@@ -161,6 +164,21 @@ def gemm(a_srcs, b_srcs, prog, *, lin, M, N, out, geo=(1, 1), bias=None, rowvec=
 TAPS3 = [(kw - 1, kh - 1) for kh in range(3) for kw in range(3)]  # (dw, dh), tap = kh*3 + kw
 
 
+# int32 semaphores for reproducible LoRA weight gradients (pcm_wgrad_desc.sem): the token splits of
+# a wgrad tile then accumulate in split order
+WGRAD_SEM = None
+_DET = os.environ.get("PCM_DETERMINISTIC", "0") == "1"
+
+
+def deterministic(on, device=None):
+    """Bit-reproducible mode.  GroupNorm statistics, split-K, the gradient norm and the loss
+    reduction are always order independent; the LoRA weight gradients (token-split fp32 `red`)
+    additionally need this switch (or PCM_DETERMINISTIC=1), which serialises the splits of a tile."""
+    global WGRAD_SEM, _DET
+    _DET = bool(on)
+    WGRAD_SEM = torch.zeros(4096, device=device or "cuda", dtype=torch.int32) if on else None
+
+
 def wgrad(p_src, q_src, out, *, lin, M, geo=(1, 1), taps=((0, 0),), tap_off=(0,), os_row, os_col,
           alpha=1.0, q_c0=0, ksplit=0):
     """out[tap_off[t] + ch*os_row + r*os_col] += alpha * sum_m P[m(+tap t), ch] * Q[m, q_c0 + r]."""
@@ -177,6 +195,11 @@ def wgrad(p_src, q_src, out, *, lin, M, geo=(1, 1), taps=((0, 0),), tap_off=(0,)
     d.os_row, d.os_col = os_row, os_col
     d.ksplit = ksplit
     d.alpha = alpha
+    if _DET and DRY_RUN is None:
+        if WGRAD_SEM is None:
+            deterministic(True)
+        assert ((p_src.C + 127) // 128) * len(taps) <= WGRAD_SEM.numel()
+        d.sem = WGRAD_SEM.data_ptr()
     LAUNCHES["count"] += 1
     if DRY_RUN is not None:
         DRY_RUN.append(("wgrad", dict(M=M, Cp=p_src.C, taps=len(taps))))
@@ -200,19 +223,40 @@ def _call(name, *args):
     L.check(getattr(L.lib(), name)(*args, torch.cuda.current_stream().cuda_stream), name)
 
 
+_GN_WS = {}
+
+
+def gn_workspace(device, B, HW, C, G):
+    """Per-device GroupNorm scratch (block counters + per-block partial statistics), zero-initialised
+    once and grown on demand; the kernels leave the counters at zero."""
+    if DRY_RUN is not None:
+        return None, 0
+    need = L.lib().pcm_groupnorm_ws_bytes(B, HW, C, G)
+    if need < 0:
+        raise L.PcmError(L.lib().pcm_last_error().decode())
+    key = torch.device(device)
+    ws = _GN_WS.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.zeros(max(need, 8 << 20), device=device, dtype=torch.uint8)
+        _GN_WS[key] = ws
+    return ws, ws.numel()
+
+
 def groupnorm_fwd(x1, x2, gamma, beta, eps, silu, out, stats, B, HW, G=32):
     C1 = x1.shape[-1]
     C2 = x2.shape[-1] if x2 is not None else 0
+    ws, nws = gn_workspace(x1.device, B, HW, C1 + C2, G)
     _call("pcm_groupnorm_fwd", _p(x1), _p(x2), C1, C2, B, HW, G, _p(gamma), _p(beta), eps, int(silu),
-          _p(out), _p(stats))
+          _p(out), _p(stats), _p(ws), nws)
     return out
 
 
 def groupnorm_bwd(dy, x1, x2, gamma, beta, eps, silu, stats, red, add, dx1, dx2, B, HW, G=32, colsum=None):
     C1 = x1.shape[-1]
     C2 = x2.shape[-1] if x2 is not None else 0
+    ws, nws = gn_workspace(x1.device, B, HW, C1 + C2, G)
     _call("pcm_groupnorm_bwd", _p(dy), _p(x1), _p(x2), C1, C2, B, HW, G, _p(gamma), _p(beta), eps,
-          int(silu), _p(stats), _p(red), _p(add), _p(dx1), _p(dx2), _p(colsum))
+          int(silu), _p(stats), _p(red), _p(add), _p(dx1), _p(dx2), _p(colsum), _p(ws), nws)
 
 
 def cast_f32_bf16(x, out):

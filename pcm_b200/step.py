@@ -65,7 +65,8 @@ class PCMTrainStep:
         self.exp_avg = torch.zeros(n, **f32)
         self.exp_avg_sq = torch.zeros(n, **f32)
         self.opt_state = torch.tensor([lr, 0.0], **f32)  # lr, step
-        self.sumsq = torch.zeros(1, device=device, dtype=torch.float64)
+        # [0] = sum of squares; rest = scratch of the fixed-order reduction (PCM_SUMSQ_WS_DOUBLES)
+        self.sumsq = torch.zeros(1024, device=device, dtype=torch.float64)
         self.debug = {} if keep_debug else None
         # static input slots (graph replay copies into these)
         self.in_latents = torch.zeros(B, height, width, 4, **f32)
