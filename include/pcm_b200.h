@@ -160,13 +160,14 @@ int pcm_prepare(const float* alphas_cumprod, int num_train, int num_ddim, const 
 /* DDPMScheduler.add_noise, S15:500-524 (T15:1178) */
 int pcm_add_noise(const float* x, const float* noise, const double* coef, int64_t per, int B,
                   int bf16_mode, float* out, void* stream);
-/* predicted_origin x2 + CFG mix + DDIMSolver.ddim_step, T15:1224-1258 */
+/* predicted_origin x2 + CFG mix + DDIMSolver.ddim_step, T15:1224-1258.
+ * pred_type: 0 = epsilon, 1 = v_prediction (predicted_origin, T15:268-280) */
 int pcm_teacher_step(const float* eps_c, const float* eps_u, const float* noisy, const double* coef,
-                     int64_t per, int B, float* x_prev, void* stream);
+                     int64_t per, int B, int pred_type, float* x_prev, void* stream);
 /* T15:1200-1212 + 1269-1293: loss (0 = huber, 1 = l2), d loss / d eps_student, optional dumps */
 int pcm_loss(const float* eps_s, const float* eps_t, const float* noisy, const float* x_prev,
-             const double* coef, int64_t per, int B, int loss_type, float huber_c, float* loss_out,
-             float* d_eps, float* model_pred, float* target, void* stream);
+             const double* coef, int64_t per, int B, int loss_type, float huber_c, int pred_type,
+             float* loss_out, float* d_eps, float* model_pred, float* target, void* stream);
 /* DDPMScheduler.noise_travel, S15:526-554 */
 int pcm_noise_travel(const float* x, const float* noise, const float* alphas_cumprod,
                      const int64_t* t_cur, const int64_t* t_tgt, int64_t per, int B, float* out,
@@ -186,6 +187,9 @@ int pcm_grad_sumsq(const float* g, int64_t n, double* out, void* stream);
 int pcm_adamw_clip(float* p, float* g, float* m, float* v, int64_t n, float* state, float beta1,
                    float beta2, float eps, float weight_decay, float max_norm, float inv_world,
                    const double* sumsq, int zero_grad, void* stream);
+/* update_ema(target_params, source_params, rate), T15:344-355 (defined but never called by the
+ * reference loop; offered as the opt-in EMA target): targ = rate*targ + (1-rate)*src */
+int pcm_ema_update(float* targ, const float* src, int64_t n, float rate, void* stream);
 /* table: num_entries x 9 int64 {a_off, b_off, a_fwd, sb_fwd, sb_t, a_t, cin|taps<<32, n|r<<32,
  * work_begin}; writes bf16 operand copies A, s*B, (s*B)^T, A^T */
 int pcm_lora_refresh(const float* master, const void* table, int num_entries, int64_t total_work,

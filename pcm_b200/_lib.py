@@ -106,6 +106,7 @@ EXPORTS = [
     "pcm_axpby_f64",
     "pcm_grad_sumsq",
     "pcm_adamw_clip",
+    "pcm_ema_update",
     "pcm_lora_refresh",
 ]
 
@@ -132,12 +133,13 @@ ARGTYPES = {
     "pcm_cast_f32_bf16": [P, L64, P, P],
     "pcm_prepare": [P, I, I, P, I, P, P, I, I, P, P, P, P, P],
     "pcm_add_noise": [P, P, P, L64, I, I, P, P],
-    "pcm_teacher_step": [P, P, P, P, L64, I, P, P],
-    "pcm_loss": [P, P, P, P, P, L64, I, I, F, P, P, P, P, P],
+    "pcm_teacher_step": [P, P, P, P, L64, I, I, P, P],
+    "pcm_loss": [P, P, P, P, P, L64, I, I, F, I, P, P, P, P, P],
     "pcm_noise_travel": [P, P, P, P, P, L64, I, P, P],
     "pcm_axpby_f64": [P, P, P, P, L64, I, P, P],
     "pcm_grad_sumsq": [P, L64, P, P],
     "pcm_adamw_clip": [P, P, P, P, L64, P, F, F, F, F, F, F, P, I, P],
+    "pcm_ema_update": [P, P, L64, F, P],
     "pcm_lora_refresh": [P, P, I, L64, F, P, P],
 }
 

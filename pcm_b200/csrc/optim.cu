@@ -83,6 +83,16 @@ __global__ void adamw_clip_kernel(float* __restrict__ p, float* __restrict__ g,
   }
 }
 
+// update_ema (T15:344-355): targ = rate * targ + (1 - rate) * src   (torch: detach().mul_(rate).add_(src, alpha=1-rate))
+__global__ void ema_update_kernel(float* __restrict__ targ, const float* __restrict__ src, long long n,
+                                  float rate) {
+  griddep_sync();
+  const float a = 1.f - rate;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    targ[i] = targ[i] * rate + src[i] * a;
+}
+
 __global__ void state_step_kernel(float* state) {
   griddep_sync(); state[1] += 1.f; }
 
@@ -193,6 +203,16 @@ extern "C" int pcm_adamw_clip(float* p, float* g, float* m, float* v, int64_t n,
   CUDA_TRY(launch_pdl(adamw_clip_kernel, dim3(grid), dim3(256), 0, ST(stream), p, g, m, v, n, state, beta1, beta2, eps,
                                                   weight_decay, max_norm, inv_world, sumsq,
                                                   zero_grad));
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int pcm_ema_update(float* targ, const float* src, int64_t n, float rate, void* stream) {
+  int grid = static_cast<int>((n + 255) / 256);
+  if (grid > num_sms() * 8) grid = num_sms() * 8;
+  if (grid < 1) grid = 1;
+  CUDA_TRY(launch_pdl(ema_update_kernel, dim3(grid), dim3(256), 0, ST(stream), targ, src,
+                      static_cast<long long>(n), rate));
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

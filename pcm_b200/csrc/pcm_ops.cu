@@ -119,7 +119,8 @@ __global__ void pcm_teacher_step_kernel(const float* __restrict__ eps_c,
                                         const float* __restrict__ eps_u,
                                         const float* __restrict__ noisy,
                                         const double* __restrict__ coef, long long per,
-                                        long long total, float* __restrict__ x_prev) {
+                                        long long total, int pred_type,
+                                        float* __restrict__ x_prev) {
   griddep_sync();
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -127,8 +128,9 @@ __global__ void pcm_teacher_step_kernel(const float* __restrict__ eps_c,
     const float al = static_cast<float>(c[kAlphaS]), sg = static_cast<float>(c[kSigmaS]);
     const float w = static_cast<float>(c[kW]);
     const float ec = eps_c[i], eu = eps_u[i], xn = noisy[i];
-    const float x0c = (xn - sg * ec) / al;  // predicted_origin, epsilon (T15:272)
-    const float x0u = (xn - sg * eu) / al;
+    // predicted_origin: epsilon (T15:272) or v_prediction (T15:275)
+    const float x0c = pred_type == 0 ? (xn - sg * ec) / al : al * xn - sg * ec;
+    const float x0u = pred_type == 0 ? (xn - sg * eu) / al : al * xn - sg * eu;
     const float px0 = x0c + w * (x0c - x0u);  // T15:1254
     const float pe = ec + w * (ec - eu);      // T15:1255-1257
     const double xp = c[kAi] * static_cast<double>(px0) + c[kSi] * static_cast<double>(pe);
@@ -140,8 +142,9 @@ __global__ void pcm_teacher_step_kernel(const float* __restrict__ eps_c,
 __global__ void pcm_loss_kernel(const float* __restrict__ eps_s, const float* __restrict__ eps_t,
                                 const float* __restrict__ noisy, const float* __restrict__ x_prev,
                                 const double* __restrict__ coef, long long per, long long total,
-                                int loss_type, float huber_c, float* __restrict__ loss_out,
-                                float* __restrict__ d_eps, float* __restrict__ model_pred_out,
+                                int loss_type, float huber_c, int pred_type,
+                                float* __restrict__ loss_out, float* __restrict__ d_eps,
+                                float* __restrict__ model_pred_out,
                                 float* __restrict__ target_out) {
   griddep_sync();
   __shared__ double s_part[32];
@@ -152,10 +155,12 @@ __global__ void pcm_loss_kernel(const float* __restrict__ eps_s, const float* __
     const float es = eps_s[i], et = eps_t[i], xn = noisy[i], xp = x_prev[i];
     // student: x0 = (noisy - sigma*eps)/alpha (T15:1200-1207); jump to the phase start (T15:1209);
     // c_skip_start = 0, c_out_start = 1 (T15:256-259, 1212)
-    const float x0s = (xn - static_cast<float>(c[kSigmaS]) * es) / static_cast<float>(c[kAlphaS]);
+    const float als = static_cast<float>(c[kAlphaS]), sgs = static_cast<float>(c[kSigmaS]);
+    const float alt = static_cast<float>(c[kAlphaT]), sgt = static_cast<float>(c[kSigmaT]);
+    const float x0s = pred_type == 0 ? (xn - sgs * es) / als : als * xn - sgs * es;
     const double mp = c[kAp] * static_cast<double>(x0s) + c[kSp] * static_cast<double>(es);
     // target: same network at (x_prev, t) (T15:1263-1279), then c_skip/c_out mix (T15:1280)
-    const float x0t = (xp - static_cast<float>(c[kSigmaT]) * et) / static_cast<float>(c[kAlphaT]);
+    const float x0t = pred_type == 0 ? (xp - sgt * et) / alt : alt * xp - sgt * et;
     const double tj = c[kAp] * static_cast<double>(x0t) + c[kSp] * static_cast<double>(et);
     const double tg = c[kCskip] * static_cast<double>(xp) + (1.0 - c[kCskip]) * tj;
     const float mpf = static_cast<float>(mp), tgf = static_cast<float>(tg);  // .float() T15:1285,1290
@@ -170,8 +175,9 @@ __global__ void pcm_loss_kernel(const float* __restrict__ eps_s, const float* __
       dl = 2.f * d;
     }
     acc += static_cast<double>(l);
-    // d model_pred / d eps_s = Sp - Ap * sigma / alpha
-    const double dmp = c[kSp] - c[kAp] * c[kSigmaS] / c[kAlphaS];
+    // d model_pred / d eps_s = Sp - Ap * sigma / alpha  (v_prediction: Sp - Ap * sigma)
+    const double dmp = pred_type == 0 ? c[kSp] - c[kAp] * c[kSigmaS] / c[kAlphaS]
+                                      : c[kSp] - c[kAp] * c[kSigmaS];
     if (d_eps) d_eps[i] = static_cast<float>(static_cast<double>(dl) * inv_n * dmp);
     if (model_pred_out) model_pred_out[i] = mpf;
     if (target_out) target_out[i] = tgf;
@@ -246,22 +252,24 @@ extern "C" int pcm_add_noise(const float* x, const float* noise, const double* c
   return 0;
 }
 extern "C" int pcm_teacher_step(const float* eps_c, const float* eps_u, const float* noisy,
-                                const double* coef, int64_t per, int B, float* x_prev,
-                                void* stream) {
+                                const double* coef, int64_t per, int B, int pred_type,
+                                float* x_prev, void* stream) {
   const long long total = per * B;
+  if (pred_type != 0 && pred_type != 1) return set_error("pcm_teacher_step: bad prediction type");
   CUDA_TRY(launch_pdl(pcm_teacher_step_kernel, dim3(grid_for(total)), dim3(256), 0, ST(stream), eps_c, eps_u, noisy, coef, per,
-                                                                   total, x_prev));
+                                                                   total, pred_type, x_prev));
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
 extern "C" int pcm_loss(const float* eps_s, const float* eps_t, const float* noisy,
                         const float* x_prev, const double* coef, int64_t per, int B, int loss_type,
-                        float huber_c, float* loss_out, float* d_eps, float* model_pred,
-                        float* target, void* stream) {
+                        float huber_c, int pred_type, float* loss_out, float* d_eps,
+                        float* model_pred, float* target, void* stream) {
   const long long total = per * B;
+  if (pred_type != 0 && pred_type != 1) return set_error("pcm_loss: bad prediction type");
   CUDA_TRY(launch_pdl(pcm_loss_kernel, dim3(1), dim3(1024), 0, ST(stream), eps_s, eps_t, noisy, x_prev, coef, per, total,
-                                              loss_type, huber_c, loss_out, d_eps, model_pred,
-                                              target));
+                                              loss_type, huber_c, pred_type, loss_out, d_eps,
+                                              model_pred, target));
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

@@ -43,6 +43,7 @@ _NUM_SMS = None
 # kernel-launch accounting (bench.py `gpu_launches`) and optional per-launch GEMM profiling
 LAUNCHES = {"count": 0}
 PROFILE = None  # list of (start_event, end_event, flops) when enabled
+PROFILE_EXTERNAL = False  # True: events become event-record NODES when captured in a CUDA graph
 DRY_RUN = None  # list: record (kind, info) instead of launching (shape analysis without a GPU)
 _KERNELS_PER_CALL = {"pcm_groupnorm_fwd": 2, "pcm_groupnorm_bwd": 2, "pcm_attn_bwd": 3, "pcm_adamw_clip": 2}
 
@@ -151,7 +152,8 @@ def gemm(a_srcs, b_srcs, prog, *, lin, M, N, out, geo=(1, 1), bias=None, rowvec=
                                      b_N=[b.N for b in b_srcs])))
         return out
     if PROFILE is not None:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0 = torch.cuda.Event(enable_timing=True, external=PROFILE_EXTERNAL)
+        e1 = torch.cuda.Event(enable_timing=True, external=PROFILE_EXTERNAL)
         e0.record()
         L.check(L.lib().pcm_gemm(C.byref(d), _stream()), "pcm_gemm")
         e1.record()

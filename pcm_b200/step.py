@@ -9,7 +9,7 @@ import os
 import numpy as np
 import torch
 
-from . import ops
+from . import dp, ops
 from .config import UNetConfig
 from .unet import UNetB200
 
@@ -35,7 +35,14 @@ class PCMTrainStep:
                  num_ddim_timesteps=50, num_train_timesteps=1000, loss_type="huber", huber_c=1e-3,
                  lr=5e-6, betas=(0.9, 0.999), adam_eps=1e-8, weight_decay=1e-2, max_grad_norm=1.0,
                  apply_cfg_solver=True, bf16_mode=True, alphas_cumprod=None, process_group=None,
-                 keep_debug=False):
+                 keep_debug=False, prediction_type="epsilon", ema_decay=None, grad_buckets=4):
+        """prediction_type: "epsilon" | "v_prediction" (predicted_origin, T15:268-280).
+        ema_decay: None (reference behaviour: the target network IS the student, update_ema is never
+        called, T15:1261-1268) or a rate in (0, 1): opt-in EMA target, updated after every optimiser
+        step as update_ema does (T15:344-355)."""
+        if prediction_type not in ("epsilon", "v_prediction"):
+            raise ValueError(f"Prediction type {prediction_type} currently not supported.")  # T15:277-278
+        self.pred_type = 0 if prediction_type == "epsilon" else 1
         self.cfg, self.dev = cfg, device
         self.B, self.H, self.W = batch, height, width
         self.per = height * width * 4
@@ -48,6 +55,10 @@ class PCMTrainStep:
         self.bf16_mode = int(bf16_mode)
         self.pg = process_group
         self.world = 1 if process_group is None else torch.distributed.get_world_size(process_group)
+        self.reducer = dp.GradReducer(self.unet.lora_grad, self.unet.block_grad_offsets().values(),
+                                      group=process_group, num_buckets=grad_buckets) if self.world > 1 else None
+        self.ema_decay = ema_decay
+        self.ema_master = self.unet.lora_master.clone() if ema_decay is not None else None
         acp = sd15_alphas_cumprod(num_train_timesteps) if alphas_cumprod is None else alphas_cumprod
         self.acp = acp.float().to(device)
         self.inf_idx = torch.from_numpy(inference_indices(num_ddim_timesteps, multiphase)).to(device)
@@ -84,6 +95,9 @@ class PCMTrainStep:
         self.noisy = self.noisy3[:B]
         self.start_t3 = torch.zeros(3 * B, **i64)
         self.merged = os.environ.get("PCM_MERGE_PASSES", "1") != "0"
+        # data parallel: overlap the gradient all-reduce with the backward pass (PCM_DP_OVERLAP=0: one
+        # flat all-reduce after the backward)
+        self._overlap = os.environ.get("PCM_DP_OVERLAP", "1") != "0"
         self.graph = None
         self.graph_opt = None
 
@@ -121,20 +135,38 @@ class PCMTrainStep:
             else:
                 eps_c = u.forward(self.noisy, self.start_t, self.in_prompt, lora=False)
                 eps_u = eps_c
-        ops._call("pcm_teacher_step", eps_c.data_ptr(), eps_u.data_ptr(), self.noisy.data_ptr(),
-                  self.coef.data_ptr(), per, B, self.x_prev.data_ptr())
+        self.teacher_step_kernel(eps_c, eps_u)
+        if self.ema_master is not None:      # opt-in EMA target: same network, EMA LoRA factors
+            u.refresh_lora(self.ema_master)
         eps_t = u.forward(self.x_prev, self.t, self.in_prompt, lora=True)
-        ops._call("pcm_loss", eps_s.data_ptr(), eps_t.data_ptr(), self.noisy.data_ptr(), self.x_prev.data_ptr(),
-                  self.coef.data_ptr(), per, B, self.loss_type, self.huber_c, self.loss.data_ptr(),
-                  self.d_eps.data_ptr(), ops._p(self.model_pred), ops._p(self.target))
+        if self.ema_master is not None:
+            u.refresh_lora()
+        self.loss_kernel(eps_s, eps_t)
         if self.debug is not None:
             self.debug.update(eps_student=eps_s, eps_cond=eps_c, eps_uncond=eps_u, eps_target=eps_t)
-        u.backward(self.d_eps)
+        if self.reducer is not None and self._overlap:
+            # data parallel: bucketed all-reduce(SUM) launched from inside the backward pass
+            self.reducer.start()
+            u.backward(self.d_eps, grad_ready=self.reducer.ready)
+            self.reducer.finish()
+        else:
+            u.backward(self.d_eps)
+
+    def teacher_step_kernel(self, eps_c, eps_u):
+        """x_prev <- DDIM step of the CFG-mixed teacher prediction (T15:1224-1258), one launch."""
+        ops._call("pcm_teacher_step", eps_c.data_ptr(), eps_u.data_ptr(), self.noisy.data_ptr(),
+                  self.coef.data_ptr(), self.per, self.B, self.pred_type, self.x_prev.data_ptr())
+
+    def loss_kernel(self, eps_s, eps_t):
+        """loss, d loss / d eps_student (+ model_pred / target dumps) (T15:1200-1212, 1269-1293)."""
+        ops._call("pcm_loss", eps_s.data_ptr(), eps_t.data_ptr(), self.noisy.data_ptr(), self.x_prev.data_ptr(),
+                  self.coef.data_ptr(), self.per, self.B, self.loss_type, self.huber_c, self.pred_type,
+                  self.loss.data_ptr(), self.d_eps.data_ptr(), ops._p(self.model_pred), ops._p(self.target))
 
     def optimizer_step(self):
-        if self.world > 1:
+        if self.world > 1 and not self._overlap:
             # ONE collective per step: SUM of the flat LoRA gradient; 1/world is folded into AdamW
-            torch.distributed.all_reduce(self.unet.lora_grad, group=self.pg)
+            dp.allreduce_flat_grad(self.unet.lora_grad, self.pg)
         self._optimizer_kernels()
 
     def _optimizer_kernels(self):
@@ -145,6 +177,9 @@ class PCMTrainStep:
                   self.exp_avg_sq.data_ptr(), g.numel(), self.opt_state.data_ptr(), self.betas[0],
                   self.betas[1], self.adam_eps, self.wd, self.max_norm, 1.0 / self.world,
                   self.sumsq.data_ptr(), 1)
+        if self.ema_master is not None:   # update_ema(target, source, rate): targ = rate*targ + (1-rate)*src
+            ops._call("pcm_ema_update", self.ema_master.data_ptr(), u.lora_master.data_ptr(),
+                      self.ema_master.numel(), float(self.ema_decay))
         u.refresh_lora()
 
     def run_eager(self, optimizer=True):
@@ -168,7 +203,10 @@ class PCMTrainStep:
         torch.cuda.synchronize()
         self.graph, self.graph_opt = None, None
         n0 = ops.LAUNCHES["count"]
-        if self.world == 1 or os.environ.get("PCM_NCCL_IN_GRAPH", "0") == "1":
+        in_graph = self.world == 1 or os.environ.get("PCM_NCCL_IN_GRAPH", "1") == "1"
+        if in_graph:
+            # ONE graph for the whole iteration; data parallel: the bucketed NCCL all-reduces are
+            # captured on their side streams inside it (PCM_NCCL_IN_GRAPH=0 keeps them eager)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 self.run_eager()
@@ -177,10 +215,12 @@ class PCMTrainStep:
             # data parallel: keep the collective outside the graphs (robust across NCCL versions):
             # graph(forward + backward) -> eager all_reduce -> graph(clip + AdamW + LoRA refresh)
             g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            ov, self._overlap = self._overlap, False
             with torch.cuda.graph(g1):
                 self.forward_backward()
             with torch.cuda.graph(g2):
                 self._optimizer_kernels()
+            self._overlap = ov
             self.graph, self.graph_opt = g1, g2
         ops.LAUNCHES["per_step"] = ops.LAUNCHES["count"] - n0
         # the warm-up / capture runs must not count as training steps
@@ -188,6 +228,8 @@ class PCMTrainStep:
         self.exp_avg.copy_(snap[1])
         self.exp_avg_sq.copy_(snap[2])
         self.opt_state.copy_(snap[3])
+        if self.ema_master is not None:
+            self.ema_master.copy_(snap[0])
         self.unet.lora_grad.zero_()
         self.unet.refresh_lora()
         return self.graph
@@ -208,6 +250,30 @@ class PCMTrainStep:
             self.graph.replay()
         else:
             self.graph.replay()
-            torch.distributed.all_reduce(self.unet.lora_grad, group=self.pg)
+            dp.allreduce_flat_grad(self.unet.lora_grad, self.pg)
             self.graph_opt.replay()
         return self.loss
+
+    # -- training state (accelerator.save_state / load_state, T15:1080-1105, 1308-1343) -----------
+    def state_dict(self):
+        """LoRA masters, AdamW moments, (lr, optimiser step) and the optional EMA copy."""
+        sd = dict(lora_master=self.unet.lora_master.detach().cpu().clone(),
+                  exp_avg=self.exp_avg.cpu().clone(), exp_avg_sq=self.exp_avg_sq.cpu().clone(),
+                  opt_state=self.opt_state.cpu().clone())
+        if self.ema_master is not None:
+            sd["ema_master"] = self.ema_master.cpu().clone()
+        return sd
+
+    def load_state_dict(self, sd):
+        n = self.unet.lora_master.numel()
+        for k in ("lora_master", "exp_avg", "exp_avg_sq"):
+            if sd[k].numel() != n:
+                raise ValueError(f"checkpoint tensor {k} has {sd[k].numel()} elements, expected {n}")
+        self.unet.lora_master.copy_(sd["lora_master"])
+        self.exp_avg.copy_(sd["exp_avg"])
+        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        self.opt_state.copy_(sd["opt_state"])
+        if self.ema_master is not None:
+            self.ema_master.copy_(sd.get("ema_master", sd["lora_master"]))
+        self.unet.lora_grad.zero_()
+        self.unet.refresh_lora()

@@ -8,19 +8,27 @@ Keeps the reference script's command line (flag names / defaults of
 encoders, validation image logging, hub upload.  Inputs to the step are therefore either
   --synthetic            seeded random latents / text embeddings (benchmark + parity mode), or
   --latent_cache DIR     *.pt files holding {"latents" [B,4,h,w], "prompt_embeds" [B,77,768]}
-                         produced upstream by the reference's own VAE/CLIP preprocessing.
+                         produced upstream by the reference's own VAE/CLIP preprocessing, plus the CLIP
+                         encoding of the empty prompt (T15:1053-1059) either per file
+                         ("uncond_prompt_embeds" [B or 1,77,768]) or once via --uncond_embeds FILE.
+Checkpoints `checkpoint-N/` hold the LoRA adapter AND the optimiser state (AdamW moments, step, lr,
+host RNG), rotate under --checkpoints_total_limit and resume with --resume_from_checkpoint
+(accelerator.save_state / load_state semantics, T15:1080-1105, 1308-1343).
 Launch: `python -m pcm_b200.train_pcm_lora_sd15 ...` or
 `python -m torch.distributed.run --nproc-per-node N -m pcm_b200.train_pcm_lora_sd15 ...`.
 """
 import argparse
 import glob
 import json
+import math
 import os
+import shutil
+import sys
 import time
 
 import torch
 
-from . import config, weights
+from . import config, dp, lr_schedules, weights
 from .step import PCMTrainStep
 
 
@@ -82,8 +90,14 @@ def parse_args(argv=None):
     # ---- additions of this implementation ----
     p.add_argument("--synthetic", action="store_true", help="seeded synthetic latents / text embeddings")
     p.add_argument("--latent_cache", type=str, default=None)
+    p.add_argument("--uncond_embeds", type=str, default=None,
+                   help=".pt tensor [1 or B,77,768]: CLIP encoding of the empty prompt (T15:1053-1059)")
     p.add_argument("--no_cuda_graph", action="store_true")
     p.add_argument("--log_every", type=int, default=10)
+    p.add_argument("--prediction_type", type=str, default="epsilon", choices=["epsilon", "v_prediction"],
+                   help="noise_scheduler.config.prediction_type of the teacher (T15:1204, 1228)")
+    p.add_argument("--ema_decay", type=float, default=None,
+                   help="opt-in EMA target (update_ema, T15:344-355); default: target = student like the reference")
     args = p.parse_args(argv)
     env_local_rank = int(os.environ.get("LOCAL_RANK", -1))   # same override as the reference
     if env_local_rank != -1 and env_local_rank != args.local_rank:
@@ -94,32 +108,80 @@ def parse_args(argv=None):
         raise ValueError("pcm_b200 runs one optimiser step per iteration (all reference recipes use 1)")
     if args.use_8bit_adam:
         raise ValueError("--use_8bit_adam (bitsandbytes) is not provided: 180 GB HBM holds fp32 AdamW state")
+    if args.mixed_precision == "no":
+        raise ValueError("--mixed_precision no (fp32 compute) is not provided: the tcgen05 path computes with "
+                         "bf16 operands and fp32 accumulation; use bf16")
     if args.mixed_precision == "fp16":
-        raise ValueError("pcm_b200 computes in bf16 (tcgen05 kind::f16 with bf16 operands); use --mixed_precision bf16")
+        # every shipped recipe passes fp16 (train_pcm_lora_sd15.sh:9).  fp16 and bf16 run on the same
+        # tensor-core rate; this implementation stores activations as bf16 (8 exponent bits: no
+        # GradScaler / overflow skipping needed) - documented deviation, DESIGN.md section 4.
+        print("pcm_b200: --mixed_precision fp16 runs the bf16 path (same rate, wider range, no loss scaling)",
+              file=sys.stderr)
+    if args.lr_scheduler not in lr_schedules.SCHEDULES:
+        raise ValueError(f"{args.lr_scheduler} is not a valid SchedulerType, please select one of "
+                         f"{list(lr_schedules.SCHEDULES)}.")
     return args
 
 
-def _lr_at(args, step):
-    if args.lr_scheduler == "constant":
-        return args.learning_rate
-    if args.lr_scheduler == "constant_with_warmup":
-        return args.learning_rate * min(1.0, (step + 1) / max(1, args.lr_warmup_steps))
-    raise ValueError(f"lr scheduler {args.lr_scheduler} not supported")
+def _lr_at(args, step, world=1):
+    """Learning rate of optimiser step `step` (0-based): diffusers get_scheduler(...) as stepped by
+    accelerate (T15:1026-1031, 1300)."""
+    return lr_schedules.lr_at(args.lr_scheduler, args.learning_rate, step, args.lr_warmup_steps,
+                              args.max_train_steps, num_processes=world)
+
+
+def find_resume_path(output_dir, resume_from_checkpoint):
+    """T15:1082-1090: explicit path -> its basename; "latest" -> highest checkpoint-N in output_dir."""
+    if resume_from_checkpoint != "latest":
+        return os.path.basename(resume_from_checkpoint)
+    if not os.path.isdir(output_dir):
+        return None
+    dirs = [d for d in os.listdir(output_dir) if d.startswith("checkpoint")]
+    dirs = sorted(dirs, key=lambda x: int(x.split("-")[1]))
+    return dirs[-1] if len(dirs) > 0 else None
+
+
+def rotate_checkpoints(output_dir, total_limit):
+    """T15:1311-1337: before saving, keep at most `total_limit - 1` existing checkpoints."""
+    if total_limit is None:
+        return
+    ckpts = [d for d in os.listdir(output_dir) if d.startswith("checkpoint")]
+    ckpts = sorted(ckpts, key=lambda x: int(x.split("-")[1]))
+    if len(ckpts) >= total_limit:
+        for d in ckpts[0:len(ckpts) - total_limit + 1]:
+            shutil.rmtree(os.path.join(output_dir, d))
+
+
+def save_state(st, cfg, path, global_step, gen):
+    """accelerator.save_state (T15:1339-1341): adapter weights + optimiser state + RNG."""
+    save_lora(st, cfg, path)
+    sd = st.state_dict()
+    sd.update(global_step=global_step, rng_state=gen.get_state())
+    torch.save(sd, os.path.join(path, "pcm_b200_state.pt"))
+
+
+def load_state(st, path, gen):
+    """accelerator.load_state (T15:1099-1100)."""
+    f = os.path.join(path, "pcm_b200_state.pt")
+    if not os.path.exists(f):
+        raise FileNotFoundError(f"{f} not found: checkpoints written before optimiser state was saved cannot be resumed")
+    sd = torch.load(f)
+    st.load_state_dict(sd)
+    gen.set_state(sd["rng_state"])
+    return int(sd["global_step"])
 
 
 def main(args):
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank, world, _ = dp.env_rank_world()
     local = max(args.local_rank, 0)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     pg = None
     if world > 1:
-        torch.distributed.init_process_group("nccl", device_id=dev)
-        pg = torch.distributed.group.WORLD
+        pg = dp.init_process_group("nccl", dev)
     if args.seed is not None:
-        torch.manual_seed(args.seed + rank)        # set_seed(args.seed + process_index)
-    cfg = config.UNetConfig(lora_rank=args.lora_rank)
+        torch.manual_seed(dp.rank_seed(args.seed, rank))        # set_seed(args.seed + process_index)
+    cfg = config.UNetConfig(lora_rank=args.lora_rank) if not getattr(args, "_cfg", None) else args._cfg
     if args.pretrained_teacher_model:
         from safetensors.torch import load_file
         sd = load_file(os.path.join(args.pretrained_teacher_model, "unet", "diffusion_pytorch_model.safetensors"))
@@ -129,55 +191,100 @@ def main(args):
         sd = weights.synthetic_state_dict(cfg, args.seed or 0)
     hw = args.resolution // 8
     B = args.train_batch_size
-    lr = args.learning_rate * (B * world if args.scale_lr else 1)
-    args.learning_rate = lr
+    # --scale_lr is declared by the reference (T15:535-540) but never read: it has no effect there either
     st = PCMTrainStep(cfg, sd, dev, batch=B, height=hw, width=hw, multiphase=args.multiphase,
                       num_ddim_timesteps=args.num_ddim_timesteps, loss_type=args.loss_type,
-                      huber_c=args.huber_c, lr=lr, betas=(args.adam_beta1, args.adam_beta2),
+                      huber_c=args.huber_c, lr=args.learning_rate, betas=(args.adam_beta1, args.adam_beta2),
                       adam_eps=args.adam_epsilon, weight_decay=args.adam_weight_decay,
                       max_grad_norm=args.max_grad_norm, apply_cfg_solver=not args.not_apply_cfg_solver,
-                      process_group=pg)
+                      process_group=pg, prediction_type=args.prediction_type, ema_decay=args.ema_decay)
     del sd
     files = sorted(glob.glob(os.path.join(args.latent_cache, "*.pt"))) if args.latent_cache else []
     if not files and not args.synthetic:
         raise SystemExit("need --synthetic or --latent_cache (the image/VAE/CLIP pipeline is out of scope)")
-    gen = torch.Generator().manual_seed((args.seed or 0) + rank)
-    uncond = torch.zeros(B, 77, cfg.cross_attention_dim)
+    gen = torch.Generator().manual_seed(dp.rank_seed(args.seed or 0, rank))
+    uncond = None
+    if args.uncond_embeds:
+        uncond = torch.load(args.uncond_embeds).float().reshape(-1, 77, cfg.cross_attention_dim)
+    elif args.synthetic:
+        # synthetic stand-in for text_encoder([""] * B): one embedding repeated over the batch
+        uncond = torch.randn(1, 77, cfg.cross_attention_dim, generator=torch.Generator().manual_seed(3))
+
+    # T15:1018-1024: steps per epoch = len(dataloader); max_train_steps defaults to epochs * that
+    if files:
+        steps_per_epoch = max(1, math.ceil(len(files) / world))
+    elif args.max_train_samples:
+        steps_per_epoch = max(1, math.ceil(args.max_train_samples / (B * world)))
+    else:
+        steps_per_epoch = None
+    if args.max_train_steps is None:
+        if steps_per_epoch is None:
+            raise SystemExit("--synthetic needs --max_train_steps (or --max_train_samples for an epoch length)")
+        args.max_train_steps = args.num_train_epochs * steps_per_epoch
 
     def next_batch(i):
         if files:
             d = torch.load(files[(i * world + rank) % len(files)])
             lat, pe = d["latents"].float(), d["prompt_embeds"].float()
             unc = d.get("uncond_prompt_embeds", uncond)
+            if unc is None:
+                raise SystemExit(
+                    "the CFG-augmented solver needs the CLIP encoding of the empty prompt (T15:1053-1059, "
+                    "1237-1258): put `uncond_prompt_embeds` into the cache files or pass --uncond_embeds")
+            unc = unc.float().reshape(-1, 77, cfg.cross_attention_dim)
         else:
             lat = torch.randn(B, 4, hw, hw, generator=gen)
             pe = torch.randn(B, 77, cfg.cross_attention_dim, generator=gen)
             unc = uncond
+        if unc.shape[0] == 1:
+            unc = unc.repeat(B, 1, 1)
         noise = torch.randn(B, 4, hw, hw, generator=gen)
         index = torch.randint(0, args.num_ddim_timesteps, (B,), generator=gen)
         w = (args.w_max - args.w_min) * torch.rand(B, generator=gen) + args.w_min
         nhwc = lambda x: x.permute(0, 2, 3, 1).contiguous()
         return nhwc(lat), nhwc(noise), index, w, pe.bfloat16(), unc.bfloat16()
 
-    st.load_inputs(*next_batch(0))
-    if not args.no_cuda_graph and world == 1:
-        st.capture()
-    max_steps = args.max_train_steps or 1000
     os.makedirs(args.output_dir, exist_ok=True)
+    global_step = 0
+    if args.resume_from_checkpoint:                # T15:1080-1105
+        path = find_resume_path(args.output_dir, args.resume_from_checkpoint)
+        if path is None:
+            if rank == 0:
+                print(f"Checkpoint '{args.resume_from_checkpoint}' does not exist. Starting a new training run.")
+            args.resume_from_checkpoint = None
+        else:
+            if rank == 0:
+                print(f"Resuming from checkpoint {path}")
+            global_step = load_state(st, os.path.join(args.output_dir, path), gen)
+            assert global_step == int(path.split("-")[1])
+    st.load_inputs(*next_batch(global_step))
+    if not args.no_cuda_graph:
+        gs = gen.get_state()
+        st.capture()
+        gen.set_state(gs)
     t0 = time.time()
-    for step in range(max_steps):
-        st.load_inputs(*next_batch(step))
-        st.set_lr(_lr_at(args, step))
+    first = global_step
+    last_loss = None
+    while global_step < args.max_train_steps:
+        st.load_inputs(*next_batch(global_step))
+        lr = _lr_at(args, global_step, world)
+        st.set_lr(lr)
         st.step()
-        if rank == 0 and (step + 1) % args.log_every == 0:
-            print(json.dumps({"step": step + 1, "loss": st.loss.item(), "lr": _lr_at(args, step),
-                              "steps_per_s": (step + 1) / (time.time() - t0)}), flush=True)
-        if rank == 0 and (step + 1) % args.checkpointing_steps == 0:
-            save_lora(st, cfg, os.path.join(args.output_dir, f"checkpoint-{step + 1}"))
+        global_step += 1
+        if rank == 0 and global_step % args.log_every == 0:
+            last_loss = st.loss.item()
+            print(json.dumps({"step": global_step, "loss": last_loss, "lr": lr,
+                              "steps_per_s": (global_step - first) / (time.time() - t0)}), flush=True)
+        if rank == 0 and global_step % args.checkpointing_steps == 0:
+            rotate_checkpoints(args.output_dir, args.checkpoints_total_limit)
+            save_state(st, cfg, os.path.join(args.output_dir, f"checkpoint-{global_step}"), global_step, gen)
+    if world > 1:
+        torch.distributed.barrier()               # accelerator.wait_for_everyone()
     if rank == 0:
         save_lora(st, cfg, args.output_dir)
     if world > 1:
         torch.distributed.destroy_process_group()
+    return st
 
 
 def save_lora(st, cfg, out_dir):

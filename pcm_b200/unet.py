@@ -216,10 +216,31 @@ class UNetB200:
             self._keep.clear()
 
     # ------------------------------------------------------------------------------------
-    def refresh_lora(self):
-        """Regenerate the bf16 GEMM operand copies (A, s*B, (s*B)^T, A^T) from the fp32 masters."""
-        ops._call("pcm_lora_refresh", self.lora_master.data_ptr(), self.refresh_table.data_ptr(),
+    def refresh_lora(self, master=None):
+        """Regenerate the bf16 GEMM operand copies (A, s*B, (s*B)^T, A^T) from the fp32 masters
+        (`master`: another flat buffer of the same layout, e.g. an EMA copy for the target pass)."""
+        master = self.lora_master if master is None else master
+        assert master.numel() == self.lora_master.numel() and master.dtype == torch.float32
+        ops._call("pcm_lora_refresh", master.data_ptr(), self.refresh_table.data_ptr(),
                   self.refresh_table.shape[0], self.refresh_work, self.scale, self.lora_opnd.data_ptr())
+
+    def block_grad_offsets(self):
+        """First flat-buffer offset of every UNet block (resnet / transformer / resample conv) that owns
+        LoRA layers, ascending - the bucket boundaries of the overlapped gradient all-reduce."""
+        offs = {}
+        for L in self.lora_layers:
+            blk = self._block_of(L.name)
+            offs[blk] = min(offs.get(blk, 1 << 62), L.lora.a_off)
+        return offs
+
+    @staticmethod
+    def _block_of(layer_name):
+        parts = layer_name.split(".")
+        if parts[0] == "mid_block":
+            return ".".join(parts[:3])
+        if parts[2] in ("downsamplers", "upsamplers"):
+            return ".".join(parts[:5])
+        return ".".join(parts[:4])
 
     def lora_state_dict(self):
         """peft-style tensors (`<module>.lora_A.weight` [r, cin(,k,k)], `.lora_B.weight`)."""
@@ -740,10 +761,14 @@ class UNetB200:
         dx, _ = self.gn_bwd(gn, dg, add=do)
         return dx.view(B, H, W, C)
 
-    def backward(self, d_eps):
+    def backward(self, d_eps, grad_ready=None):
         """d_eps: fp32 [B,H,W,4] gradient of the loss w.r.t. the student epsilon.
-        Accumulates LoRA gradients into self.lora_grad (caller zeroes it between steps)."""
+        Accumulates LoRA gradients into self.lora_grad (caller zeroes it between steps).
+        grad_ready(offset): called (on the weight-gradient stream) after each block's backward with
+        the flat-buffer offset from which every gradient element is final."""
         tape, marks, (B, H, W) = self.saved
+        boffs = self.block_grad_offsets() if grad_ready is not None else None
+        pending = []
         cfg = self.cfg
         c0 = cfg.block_out_channels[0]
         Lco = self.layers["conv_out"]
@@ -757,8 +782,16 @@ class UNetB200:
 
         def pop():
             nonlocal mi
+            # the block popped previously has been fully enqueued by now: its gradients are final once
+            # the weight-gradient stream drains
+            if grad_ready is not None and pending:
+                off = boffs.get(pending.pop())
+                if off is not None:
+                    with UNetB200._Side(self, ()):
+                        grad_ready(off)
             kind, name, s, e = marks[mi]
             mi -= 1
+            pending.append(name)
             return kind, tape[s:e]
 
         # up path (reverse)
@@ -811,5 +844,8 @@ class UNetB200:
                 r = self.resnet_bwd(recs, d, need_dx=not first)
                 if not first:
                     d = r[0].view(Bc, Hc, Wc, -1)
+        if grad_ready is not None:
+            with UNetB200._Side(self, ()):
+                grad_ready(0)
         self._join_side()
         self.saved = None

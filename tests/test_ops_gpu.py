@@ -58,6 +58,63 @@ def test_groupnorm_fwd_bwd(cuda, B, HW, C1, C2, silu):
         _close(dx2, gref[..., C1:], tol=2e-2)
 
 
+@pytest.mark.parametrize("B,HW,C,shift,scale", [(2, 1024, 320, 60.0, 0.5), (2, 4096, 320, -200.0, 1.0),
+                                                 (3, 256, 1280, 30.0, 0.25)])
+def test_groupnorm_large_mean(cuda, B, HW, C, shift, scale):
+    """|mean| >> sigma (pretrained SD1.5 activations have such outlier channels): a one-pass
+    E[x^2] - mean^2 variance in fp32 loses the variance to cancellation; the pivot-shifted / Chan
+    statistics must match torch's Welford-style group_norm, forward and backward, eps = 1e-6."""
+    from pcm_b200 import ops
+    x = _rand((B, HW, C), cuda, 5, scale, shift)
+    gamma = torch.randn(C, device=cuda) * 0.2 + 1
+    beta = torch.randn(C, device=cuda) * 0.2
+    out = torch.empty(B, HW, C, device=cuda, dtype=BF)
+    stats = torch.empty(B, 32, 2, device=cuda)
+    ops.groupnorm_fwd(x, None, gamma, beta, 1e-6, False, out, stats, B, HW)
+    xin = x.double().requires_grad_(True)
+    ref = F.group_norm(xin.transpose(1, 2), 32, gamma.double(), beta.double(), 1e-6).transpose(1, 2)
+    _close(out, ref)
+    xg = xin.detach().view(B, HW, 32, C // 32)
+    mean = xg.mean(dim=(1, 3))
+    rstd = (xg.var(dim=(1, 3), unbiased=False) + 1e-6).rsqrt()
+    assert torch.allclose(stats[..., 0].double(), mean, rtol=1e-5, atol=1e-5)
+    assert torch.allclose(stats[..., 1].double(), rstd, rtol=2e-4), (stats[..., 1].double() / rstd - 1).abs().max()
+    dy = _rand((B, HW, C), cuda, 6)
+    ref.backward(dy.double())
+    dx = torch.empty_like(x)
+    red = torch.empty(B, 32, 2, device=cuda)
+    ops.groupnorm_bwd(dy, x, None, gamma, beta, 1e-6, False, stats, red, None, dx, None, B, HW)
+    _close(dx, xin.grad, tol=2e-2)
+
+
+def test_groupnorm_reproducible_and_colsum(cuda):
+    """Statistics, backward sums and per-image column sums are merged in block order: repeated
+    launches are bit-identical; the column sums match a float64 reference."""
+    from pcm_b200 import ops
+    B, HW, C = 3, 1024, 640
+    x = _rand((B, HW, C), cuda, 1, 1.5, 0.3)
+    dy = _rand((B, HW, C), cuda, 3)
+    gamma = torch.randn(C, device=cuda) * 0.2 + 1
+    beta = torch.randn(C, device=cuda) * 0.2
+    runs = []
+    for _ in range(4):
+        out = torch.empty(B, HW, C, device=cuda, dtype=BF)
+        stats = torch.empty(B, 32, 2, device=cuda)
+        ops.groupnorm_fwd(x, None, gamma, beta, 1e-5, True, out, stats, B, HW)
+        dx = torch.empty_like(x)
+        red = torch.empty(B, 32, 2, device=cuda)
+        cs = torch.empty(B, C, device=cuda)
+        ops.groupnorm_bwd(dy, x, None, gamma, beta, 1e-5, True, stats, red, None, dx, None, B, HW, colsum=cs)
+        torch.cuda.synchronize()
+        runs.append((out, stats, dx, red, cs))
+    for r in runs[1:]:
+        for a, b in zip(runs[0], r):
+            assert torch.equal(a, b)
+    dx, cs = runs[0][2], runs[0][4]
+    # the kernel sums its unrounded fp32 dx; the bf16-rounded dx differs by rounding noise only
+    assert torch.allclose(cs.double(), dx.double().sum(1), rtol=2e-2, atol=2e-2 * dx.double().sum(1).abs().max().item())
+
+
 @pytest.mark.parametrize("M,C", [(1000, 320), (256, 1280), (77, 64), (512, 640)])
 def test_layernorm_fwd_bwd(cuda, M, C):
     from pcm_b200 import ops
