@@ -71,6 +71,14 @@ typedef struct {
   int32_t ksplit;        /* > 1: split the K program over ksplit CTAs per tile (small-M, long-K) */
   void* splitk_ws;       /* fp32 [ksplit, M, N] scratch: one slice of partial sums per K split, added in
                             split order by the finalize kernel (required if ksplit > 1) */
+  int32_t dep_a_src1;    /* 1 + index of the ONLY A source written by the kernel launched immediately
+                            before this one on the stream (the layer's LoRA down-projection T), 0 = none.
+                            When set, the kernel starts under programmatic dependent launch without
+                            waiting for that kernel and only waits right before the first TMA read of
+                            this source; M tiles are visited last-to-first so that rows which do not
+                            carry the adapter (teacher samples of the merged pass) run while the
+                            down-projection is still in flight. Every other input must come from older
+                            launches. */
 } pcm_gemm_desc;
 
 /* LoRA weight-gradient descriptor: out[ch, r] += alpha * sum_m P[m(+tap), ch] * Q[m, r], r < 64.

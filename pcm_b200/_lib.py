@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libpcm_b200.so")
+# PCM_B200_LIB: alternative build of the same C ABI (kernel experiments); default = the in-tree library
+LIB_PATH = os.environ.get("PCM_B200_LIB") or os.path.join(_HERE, "lib", "libpcm_b200.so")
 
 MAX_ASRC, MAX_BSRC, MAX_PROG = 6, 4, 24
 SUMSQ_WS_DOUBLES = 1024   # PCM_SUMSQ_WS_DOUBLES
@@ -37,6 +38,7 @@ class GemmDesc(C.Structure):
         ("osW", C.c_int64), ("osH", C.c_int64), ("osB", C.c_int64), ("rowvec_ld", C.c_int64),
         ("epiW", C.c_int32), ("epiHW", C.c_int32), ("out_fp32", C.c_int32), ("round_bf16", C.c_int32),
         ("alpha", C.c_float), ("act", C.c_int32), ("ksplit", C.c_int32), ("splitk_ws", C.c_void_p),
+        ("dep_a_src1", C.c_int32),
     ]
 
 

@@ -47,6 +47,14 @@ __device__ __forceinline__ void griddep_sync() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
+// The two halves separately, for kernels that only depend on the previous launch through ONE late
+// input (pcm_gemm with dep_a_src1): trigger the dependents at once, wait right before that input.
+__device__ __forceinline__ void griddep_launch() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void griddep_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
 
 // ---------------- mbarrier ----------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -105,6 +113,25 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* desc, ui
       : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar)),
         "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
+}
+
+// TMA tensor store (shared -> global), bulk-group completion
+__device__ __forceinline__ void tma_store_4d(const void* desc, uint32_t smem_src, int c0, int c1, int c2,
+                                             int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               :
+               : "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {  // all but the N most recent groups read smem
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() {
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // ---------------- tcgen05 / TMEM ----------------

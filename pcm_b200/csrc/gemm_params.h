@@ -9,11 +9,14 @@ namespace pcm {
 struct KEntry {
   int a_map, b_map, dw, dh, nchunks, a_c0, b_k0;
   unsigned short n_lo, n_hi;  // n_hi > 0: entry applies to tiles with n_lo <= n0 < n_hi only
+  int m_hi;                   // > 0: entry applies to tiles with m0 < m_hi only (its A source has
+                              // fewer rows than the output: LoRA T of the leading samples)
 };
 
 struct alignas(64) GemmParams {
   CUtensorMap a_maps[PCM_MAX_ASRC];
   CUtensorMap b_maps[PCM_MAX_BSRC];
+  CUtensorMap out_map, res_map;  // epilogue v2: [32 col x 32 row] SWIZZLE_64B boxes of out / residual
   KEntry prog[PCM_MAX_PROG];
   int num_prog, lin;
   int M, N;
@@ -28,6 +31,7 @@ struct alignas(64) GemmParams {
   int out_fp32, round_bf16;
   float alpha;
   int act;
+  int dep_a_map;     // >= 0: A map written by the previous launch (late PDL wait), -1: none
   int filtered;      // some K entries carry an N range (per-tile K-block count varies)
   int ksplit;        // > 1: work item = (tile, K split); split s stores its fp32 partial sums to
   float* ws;         // ws[s][m * N + n]; the finalize kernel adds the slices in order and applies

@@ -19,6 +19,7 @@
 #include "../../include/pcm_b200.h"
 #include "gemm_params.h"
 #include "gemm_epilogue.cuh"
+#include "gemm_epilogue_v2.cuh"
 
 namespace pcm {
 
@@ -30,8 +31,8 @@ constexpr int kMaxStages = 8;
 constexpr int kStagingBytes = 2 * 128 * 32 * 4;  // epilogue transposition buffers (fp32)
 constexpr int kSmemLimit = 227 * 1024 - 512;     // dynamic smem budget (227 KB max minus static)
 
-__global__ void __launch_bounds__(kGemmThreads, 1)
-pcm_gemm_kernel(const __grid_constant__ GemmParams p) {
+template <bool EPI2>
+__device__ __forceinline__ void gemm_body(const GemmParams& p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -39,6 +40,7 @@ pcm_gemm_kernel(const __grid_constant__ GemmParams p) {
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
   __shared__ __align__(8) uint64_t tfull_bar[2];
   __shared__ __align__(8) uint64_t tempty_bar[2];
+  __shared__ __align__(8) uint64_t rbar[8][2];  // epilogue v2: residual boxes (per warp, 2 in flight)
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5;
@@ -59,6 +61,14 @@ pcm_gemm_kernel(const __grid_constant__ GemmParams p) {
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 8);
     }
+    if (EPI2) {
+      tma_prefetch_desc(&p.out_map);
+      tma_prefetch_desc(&p.res_map);
+      for (int i = 0; i < 8; ++i) {
+        mbar_init(&rbar[i][0], 1);
+        mbar_init(&rbar[i][1], 1);
+      }
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -69,17 +79,25 @@ pcm_gemm_kernel(const __grid_constant__ GemmParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
-  griddep_sync();  // PDL: everything above overlapped the previous kernel's tail
+  // PDL: everything above overlapped the previous kernel's tail.  With a late dependency
+  // (dep_a_map >= 0: only the LoRA down-projection T comes from the previous launch, everything else
+  // from launches that one has already waited for) the base K blocks start right away and only the
+  // TMA producer waits, just before its first read of T.
+  if (p.dep_a_map < 0) griddep_sync();
+  else griddep_launch();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      bool dep_waited = p.dep_a_map < 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
         const int tile = item / p.ksplit, ks = item - tile * p.ksplit;
         const int kb0 = ks * kb_per, kb1 = min(p.num_kblocks, kb0 + kb_per);
-        const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
+        int tm = tile / p.tiles_n;
+        const int tn = tile - tm * p.tiles_n;
+        if (p.dep_a_map >= 0) tm = p.tiles_m - 1 - tm;  // adapter-free rows first (see dep_a_src1)
         const int m0 = tm * 128, n0 = tn * p.block_n;
         int b0 = 0, h0 = 0;
         if (!p.lin) {
@@ -90,9 +108,14 @@ pcm_gemm_kernel(const __grid_constant__ GemmParams p) {
         for (int e = 0; e < p.num_prog; ++e) {
           const KEntry en = p.prog[e];
           if (en.n_hi != 0 && (n0 < en.n_lo || n0 >= en.n_hi)) continue;  // other layer's K block
+          if (en.m_hi != 0 && m0 >= en.m_hi) continue;  // rows past the end of this entry's A source
           if (kidx + en.nchunks <= kb0 || kidx >= kb1) {  // entry entirely outside this K split
             kidx += en.nchunks;
             continue;
+          }
+          if (!dep_waited && en.a_map == p.dep_a_map) {
+            griddep_wait();  // the previous launch (T = x A^T) is complete and visible
+            dep_waited = true;
           }
           for (int c = 0; c < en.nchunks; ++c, ++kidx) {
             if (kidx < kb0 || kidx >= kb1) continue;
@@ -125,12 +148,16 @@ pcm_gemm_kernel(const __grid_constant__ GemmParams p) {
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
         const int ks = item % p.ksplit;
         int nkb = min(p.num_kblocks, (ks + 1) * kb_per) - ks * kb_per;
-        if (p.filtered) {  // N-ranged entries (ksplit == 1): count the K blocks of this tile
-          const int n0 = (item % p.tiles_n) * p.block_n;
+        if (p.filtered) {  // N- or M-ranged entries (ksplit == 1): count the K blocks of this tile
+          int tm = item / p.tiles_n;
+          const int n0 = (item - tm * p.tiles_n) * p.block_n;
+          if (p.dep_a_map >= 0) tm = p.tiles_m - 1 - tm;
+          const int m0 = tm * 128;
           nkb = 0;
           for (int e = 0; e < p.num_prog; ++e) {
             const KEntry en = p.prog[e];
-            if (en.n_hi == 0 || (n0 >= en.n_lo && n0 < en.n_hi)) nkb += en.nchunks;
+            if ((en.n_hi == 0 || (n0 >= en.n_lo && n0 < en.n_hi)) && (en.m_hi == 0 || m0 < en.m_hi))
+              nkb += en.nchunks;
           }
         }
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -158,6 +185,13 @@ pcm_gemm_kernel(const __grid_constant__ GemmParams p) {
         if (acc == 0) acc_phase ^= 1;
       }
     }
+  } else if (EPI2) {
+    // ===================== epilogue v2: thread = row, TMA store / TMA residual =====================
+    const int we = warp - 2;
+    uint8_t* ebuf = smem + S * stage_bytes + we * kEpi2BytesPerWarp;
+    uint64_t* tempty = tempty_bar;
+    gemm_epilogue_v2(p, warp & 3, we >> 2, lane, tmem_base, ebuf, rbar[we], tfull_bar,
+                     [tempty](int acc) { mbar_arrive(&tempty[acc]); });
   } else {
     // ===================== epilogue =====================
     // Two phases per 32-column chunk so that global traffic is coalesced:
@@ -177,7 +211,9 @@ pcm_gemm_kernel(const __grid_constant__ GemmParams p) {
     uint32_t acc_phase = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
       const int tile = item / p.ksplit;
-      const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
+      int tm = tile / p.tiles_n;
+      const int tn = tile - tm * p.tiles_n;
+      if (p.dep_a_map >= 0) tm = p.tiles_m - 1 - tm;
       const int n0 = tn * p.block_n;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256;
       uint64_t* tempty = &tempty_bar[acc];
@@ -196,6 +232,16 @@ pcm_gemm_kernel(const __grid_constant__ GemmParams p) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
+}
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+pcm_gemm_kernel(const __grid_constant__ GemmParams p) {
+  gemm_body<false>(p);
+}
+// same mainloop with the thread-per-row / TMA-store epilogue (gemm_epilogue_v2.cuh)
+__global__ void __launch_bounds__(kGemmThreads, 1)
+pcm_gemm_epi2_kernel(const __grid_constant__ GemmParams p) {
+  gemm_body<true>(p);
 }
 
 // split-K finalize: out = act(sum over the ksplit workspace slices, in split order, + bias + rowvec
@@ -418,6 +464,54 @@ static int encode_asrc(CUtensorMap* map, const pcm_asrc& a, int lin, int geoW, i
   return encode_tmap(map, a.ptr, 4, dims, strides, box, estr);
 }
 
+static bool epi2_enabled() {
+  static int e = -1;
+  if (e < 0) {
+    const char* s = getenv("PCM_EPI_V2");
+    e = (s != nullptr && s[0] == '1') ? 1 : 0;
+  }
+  return e == 1;
+}
+
+// Tensor maps of the epilogue-v2 boxes (32 columns x 32 rows, SWIZZLE_64B) over out / residual.
+// Returns 0 and sets *ok when the row mapping fits such boxes.
+static int encode_epi2_maps(GemmParams& p, const pcm_gemm_desc* d, bool* ok) {
+  *ok = false;
+  const long long W = p.epiW, HW = p.epiHW;
+  cuuint64_t dims[4], strides[3];
+  cuuint32_t box[4] = {32, 32, 1, 1}, estr[4] = {1, 1, 1, 1};
+  if (d->osW % 8 != 0) return 0;
+  if (HW >= (1LL << 30)) {  // plain [M, N] matrix
+    dims[0] = d->N; dims[1] = d->M; dims[2] = 1; dims[3] = 1;
+    strides[0] = d->osW * 2;
+    strides[1] = strides[0] * static_cast<cuuint64_t>(d->M);
+    strides[2] = strides[1];
+  } else {
+    const long long H = HW / W;
+    if (W * H != HW || d->osH % 8 != 0 || d->osB % 8 != 0) return 0;
+    long long bw, bh, bb;
+    if (W >= 32) {
+      if (W % 32 != 0) return 0;
+      bw = 32; bh = 1; bb = 1;
+    } else {
+      if (32 % W != 0) return 0;
+      bw = W;
+      bh = (32 / W) < H ? (32 / W) : H;
+      if (H % bh != 0) return 0;
+      bb = 32 / (bw * bh);
+    }
+    if (bw * bh * bb != 32) return 0;
+    dims[0] = d->N; dims[1] = W; dims[2] = H; dims[3] = (d->M + HW - 1) / HW;
+    strides[0] = d->osW * 2; strides[1] = d->osH * 2; strides[2] = d->osB * 2;
+    box[1] = static_cast<cuuint32_t>(bw); box[2] = static_cast<cuuint32_t>(bh); box[3] = static_cast<cuuint32_t>(bb);
+  }
+  if (int rc = encode_tmap(&p.out_map, d->out, 4, dims, strides, box, estr, 64)) return rc;
+  const void* res = d->residual != nullptr ? d->residual : d->out;
+  if (int rc = encode_tmap(&p.res_map, res, 4, dims, strides, box, estr, 64)) return rc;
+  *ok = true;
+  return 0;
+}
+
 static int launch_gemm(const pcm_gemm_desc* d, cudaStream_t stream) {
   if (d->block_n < 32 || d->block_n > 256 || (d->block_n % 32) != 0)
     return set_error("pcm_gemm: block_n must be a multiple of 32 in [32, 256]");
@@ -443,7 +537,16 @@ static int launch_gemm(const pcm_gemm_desc* d, cudaStream_t stream) {
     const pcm_kentry& k = d->prog[e];
     if (k.a_src < 0 || k.a_src >= d->num_a || k.b_src < 0 || k.b_src >= d->num_b || k.nchunks < 1)
       return set_error("pcm_gemm: bad K program entry");
-    p.prog[e] = KEntry{k.a_src, k.b_src, k.dw, k.dh, k.nchunks, k.a_c0, k.b_k0, k.n_lo, k.n_hi};
+    p.prog[e] = KEntry{k.a_src, k.b_src, k.dw, k.dh, k.nchunks, k.a_c0, k.b_k0, k.n_lo, k.n_hi, 0};
+    {  // an A source with fewer rows than the output only feeds the leading M tiles (TMA would zero
+       // fill the rest: skip those K blocks instead); whole tiles only
+      const pcm_asrc& a = d->a[k.a_src];
+      const long long rows = d->lin ? a.W : static_cast<long long>(a.B) * d->geoW * d->geoH;
+      if (rows < d->M && rows % 128 == 0 && d->ksplit <= 1) {
+        p.prog[e].m_hi = static_cast<int>(rows);
+        p.filtered = 1;
+      }
+    }
     nkb += k.nchunks;
     if (k.n_hi != 0) {
       if (k.n_lo % d->block_n != 0 || (k.n_hi % d->block_n != 0 && k.n_hi < d->N) || k.n_hi <= k.n_lo)
@@ -462,7 +565,18 @@ static int launch_gemm(const pcm_gemm_desc* d, cudaStream_t stream) {
   p.tiles_n = (d->N + d->block_n - 1) / d->block_n;
   p.num_kblocks = nkb;
   const int stage_bytes = kATileBytes + d->block_n * 128;
-  int S = (kSmemLimit - 1024 - kStagingBytes) / stage_bytes;
+  // epilogue v2 (opt-in, PCM_EPI_V2=1): bf16 output, no activation, short K programs (the
+  // epilogue-bound layers; it needs 64 KB of boxes, which the long-K convolutions rather spend on
+  // pipeline stages), row mapping expressible as 32-row TMA boxes
+  bool epi2 = epi2_enabled() && !d->out_fp32 && d->act == 0 && d->N >= 32 && (d->N % 8) == 0 && nkb <= 24 &&
+              !(d->ksplit > 1 && d->splitk_ws != nullptr);
+  p.epiW = d->epiW > 0 ? d->epiW : 1;
+  p.epiHW = d->epiHW > 0 ? d->epiHW : 1;
+  if (epi2) {
+    if (int rc = encode_epi2_maps(p, d, &epi2)) return rc;
+  }
+  const int staging = epi2 ? 8 * kEpi2BytesPerWarp : kStagingBytes;
+  int S = (kSmemLimit - 1024 - staging) / stage_bytes;
   if (S > kMaxStages) S = kMaxStages;
   if (S < 2) return set_error("pcm_gemm: tile too large for shared memory");
   p.num_stages = S;
@@ -480,6 +594,7 @@ static int launch_gemm(const pcm_gemm_desc* d, cudaStream_t stream) {
   p.act = d->act;
   p.ksplit = 1;
   p.ws = nullptr;
+  p.dep_a_map = -1;
   if (d->ksplit > 1 && d->splitk_ws != nullptr && !p.filtered) {
     int ks = d->ksplit;
     if (ks > nkb) ks = nkb;
@@ -488,12 +603,18 @@ static int launch_gemm(const pcm_gemm_desc* d, cudaStream_t stream) {
     p.ksplit = ks;
   }
 
-  const size_t smem = static_cast<size_t>(S) * stage_bytes + kStagingBytes + 1024;
+  const size_t smem = static_cast<size_t>(S) * stage_bytes + staging + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     CUDA_TRY(cudaFuncSetAttribute(pcm_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   kSmemLimit));
+    CUDA_TRY(cudaFuncSetAttribute(pcm_gemm_epi2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  kSmemLimit));
     attr_set = true;
+  }
+  if (d->dep_a_src1 > 0 && p.ksplit == 1) {  // (split-K: the finalize kernel follows; keep the plain chain)
+    if (d->dep_a_src1 > d->num_a) return set_error("pcm_gemm: bad dep_a_src1");
+    p.dep_a_map = d->dep_a_src1 - 1;
   }
   const int tiles = p.tiles_m * p.tiles_n * p.ksplit;
   const int grid = tiles < num_sms() ? tiles : num_sms();
@@ -510,6 +631,11 @@ static int launch_gemm(const pcm_gemm_desc* d, cudaStream_t stream) {
     int fg = static_cast<int>((nv + 255) / 256);
     if (fg > num_sms() * 8) fg = num_sms() * 8;
     CUDA_TRY(launch_pdl(splitk_finalize_kernel, dim3(fg), dim3(256), 0, stream, f));
+    return 0;
+  }
+  if (epi2) {
+    CUDA_TRY(launch_pdl(pcm_gemm_epi2_kernel, dim3(grid), dim3(kGemmThreads), smem, stream, p));
+    CUDA_TRY(cudaGetLastError());
     return 0;
   }
   if (!p.filtered) {

@@ -52,12 +52,14 @@ static EncodeFn get_encode() {
 }
 
 int encode_tmap(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims,
-                const cuuint64_t* strides_bytes, const cuuint32_t* box, const cuuint32_t* estr) {
+                const cuuint64_t* strides_bytes, const cuuint32_t* box, const cuuint32_t* estr,
+                int swizzle_bytes) {
   EncodeFn fn = get_encode();
   if (!fn) return set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank),
                   const_cast<void*>(base), dims, strides_bytes, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char buf[256];

@@ -13,7 +13,8 @@ int num_sms();
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda
 // dependency); bf16 elements, SWIZZLE_128B, zero fill out of bounds.
 int encode_tmap(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims,
-                const cuuint64_t* strides_bytes, const cuuint32_t* box, const cuuint32_t* estr);
+                const cuuint64_t* strides_bytes, const cuuint32_t* box, const cuuint32_t* estr,
+                int swizzle_bytes = 128);
 
 bool pdl_enabled();
 

@@ -58,7 +58,7 @@ __device__ __forceinline__ void chan_merge(float& na, float& mean, float& m2, fl
   na = nn;
 }
 
-__global__ void gn_stats_kernel(const bf16* __restrict__ x1, const bf16* __restrict__ x2, int C1,
+__global__ void __launch_bounds__(512, 2) gn_stats_kernel(const bf16* __restrict__ x1, const bf16* __restrict__ x2, int C1,
                                 int C2, int HW, int G, int pix_per_block, float eps,
                                 float* __restrict__ part, unsigned* __restrict__ counters,
                                 float* __restrict__ stats) {
@@ -655,12 +655,13 @@ static inline size_t gn_ws_need(int B, int nblk, int C, int G) {
 }
 
 // Images per launch pair: the second pass over x (apply / bwd apply) should find it in L2, so a
-// pass handles at most PCM_GN_CHUNK_MB (default 24) of input at a time.
+// pass may be limited to PCM_GN_CHUNK_MB of input at a time (default 0 = one pass over all images:
+// measured on B200, bs 8 step: chunking at 24 MB costs 2.9 ms / step more than it saves).
 static int gn_chunk_images(int B, long long bytes_per_image) {
   static long long limit = -1;
   if (limit < 0) {
     const char* e = getenv("PCM_GN_CHUNK_MB");
-    limit = (e ? atoll(e) : 24) * 1024 * 1024;
+    limit = (e ? atoll(e) : 0) * 1024 * 1024;
   }
   if (limit <= 0) return B;
   long long n = limit / (bytes_per_image > 0 ? bytes_per_image : 1);

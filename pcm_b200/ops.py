@@ -40,6 +40,8 @@ def bsrc(w):
 
 
 _NUM_SMS = None
+# late programmatic-dependent-launch wait of a GEMM on its LoRA down-projection (PCM_LATE_WAIT=0: off)
+LATE_WAIT = os.environ.get("PCM_LATE_WAIT", "1") != "0"
 # kernel-launch accounting (bench.py `gpu_launches`) and optional per-launch GEMM profiling
 LAUNCHES = {"count": 0}
 PROFILE = None  # list of (start_event, end_event, flops) when enabled
@@ -89,9 +91,12 @@ def pick_tiling(M, N, nkb):
 
 def gemm(a_srcs, b_srcs, prog, *, lin, M, N, out, geo=(1, 1), bias=None, rowvec=None,
          residual=None, out_strides=None, epi=None, alpha=1.0, act=0, round_bf16=False,
-         block_n=None, ksplit=None):
+         block_n=None, ksplit=None, dep_a_src=None, splitk_ws=None):
     """Launch the tcgen05 implicit GEMM.  prog: list of (a_src, b_src, dw, dh, nchunks, a_c0, b_k0
     [, n_lo, n_hi]); an entry with n_hi > 0 only feeds output columns [n_lo, n_hi).
+
+    dep_a_src: index of the A source that the launch issued IMMEDIATELY before this one produced (the
+    layer's LoRA down-projection); the kernel then only waits for that launch right before reading it.
 
     out: bf16 or fp32 tensor; rows are addressed as b*osB + h*osH + w*osW with (osW, osH, osB) =
     out_strides (default: dense [M, ld] with ld = out.stride(-2))."""
@@ -116,7 +121,9 @@ def gemm(a_srcs, b_srcs, prog, *, lin, M, N, out, geo=(1, 1), bias=None, rowvec=
     ws = None
     if d.ksplit > 1:
         # one fp32 slice per K split (plain stores, added in split order by the finalize kernel)
-        ws = torch.empty(d.ksplit, M, N, device=out.device, dtype=torch.float32) if DRY_RUN is None else None
+        ws = splitk_ws
+        if ws is None and DRY_RUN is None:
+            ws = torch.empty(d.ksplit, M, N, device=out.device, dtype=torch.float32)
         d.splitk_ws = ws.data_ptr() if ws is not None else 0
     d.out = out.data_ptr()
     d.out_fp32 = int(out.dtype == torch.float32)
@@ -143,13 +150,14 @@ def gemm(a_srcs, b_srcs, prog, *, lin, M, N, out, geo=(1, 1), bias=None, rowvec=
     d.epiW, d.epiHW = epi
     d.alpha = alpha
     d.act = act
+    d.dep_a_src1 = 0 if (dep_a_src is None or not LATE_WAIT) else dep_a_src + 1
     LAUNCHES["count"] += 1
     if DRY_RUN is not None:
         DRY_RUN.append(("gemm", dict(M=M, N=N, K=64 * sum(e[4] for e in prog), bn=d.block_n, lin=int(lin),
                                      nprog=len(prog), res=residual is not None, ksplit=d.ksplit,
                                      prog=[tuple(e) for e in prog], num_a=len(a_srcs), num_b=len(b_srcs),
                                      a_C=[a.C for a in a_srcs], b_K=[b.K for b in b_srcs],
-                                     b_N=[b.N for b in b_srcs])))
+                                     b_N=[b.N for b in b_srcs], dep=dep_a_src)))
         return out
     if PROFILE is not None:
         e0 = torch.cuda.Event(enable_timing=True, external=PROFILE_EXTERNAL)

@@ -257,11 +257,11 @@ def main(args):
                 print(f"Resuming from checkpoint {path}")
             global_step = load_state(st, os.path.join(args.output_dir, path), gen)
             assert global_step == int(path.split("-")[1])
-    st.load_inputs(*next_batch(global_step))
+    gs = gen.get_state()                           # the capture / warm-up batch must not consume the
+    st.load_inputs(*next_batch(global_step))       # data stream (resume == uninterrupted run)
     if not args.no_cuda_graph:
-        gs = gen.get_state()
         st.capture()
-        gen.set_state(gs)
+    gen.set_state(gs)
     t0 = time.time()
     first = global_step
     last_loss = None

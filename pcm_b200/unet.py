@@ -43,6 +43,11 @@ class UNetB200:
         self.layers = {}
         self.has_lora = lora
         tab = layer_table(cfg)
+        # every resnet's time_emb_proj reads the same silu(temb): one grouped GEMM per pass
+        # (1 base K entry + one N-ranged LoRA entry per layer must fit the K program)
+        self._temb_names = [n for n, *_ in tab if n.endswith(".time_emb_proj")]
+        if not 2 <= len(self._temb_names) <= 23:
+            self._temb_names = []
         master, entries, opnd_total = [], [], 0
         moff = 0
         no_dgrad = ("attn2.to_k", "attn2.to_v", "time_emb_proj")
@@ -132,7 +137,9 @@ class UNetB200:
             self.refresh_work = work
             self.refresh_lora()
         self._build_groups(need_backward)
+        self._build_temb_group()
         self.saved = None
+        self._temb = None
         self._lb = (1, 1)
         # LoRA weight-gradient GEMMs are off the dgrad critical path (they only feed the optimiser):
         # they run on a side stream and fill SMs the main backward chain leaves idle
@@ -145,10 +152,12 @@ class UNetB200:
     _GROUPS = ((".attn1.to_q", (".attn1.to_q", ".attn1.to_k", ".attn1.to_v")),
                (".attn2.to_k", (".attn2.to_k", ".attn2.to_v")))
 
-    @classmethod
-    def _group_of(cls, name):
-        """Names of the shared-input Linear group `name` belongs to (attn1 q/k/v, attn2 k/v), or None."""
-        for _, sufs in cls._GROUPS:
+    def _group_of(self, name):
+        """Names of the shared-input Linear group `name` belongs to (attn1 q/k/v, attn2 k/v, all
+        time_emb_proj layers), or None."""
+        if name.endswith(".time_emb_proj") and self._temb_names:
+            return self._temb_names
+        for _, sufs in self._GROUPS:
             for suf in sufs:
                 if name.endswith(suf):
                     return [name[:-len(suf)] + x for x in sufs]
@@ -185,6 +194,57 @@ class UNetB200:
                     assert Ls[-1].lora.sb_fwd.data_ptr() == G.sb_stack[(g - 1) * G.cout:].data_ptr()
                     assert Ls[-1].lora.sb_t.data_ptr() == G.sbt_stack[(g - 1) * r:].data_ptr()
                 self.groups[name] = G
+
+    def _build_temb_group(self):
+        """Stacked operands of the time-embedding projections: W [sum C_i, temb], bias [sum C_i] and
+        the kind-major LoRA copies A [g*r, temb], s*B [sum C_i, r]."""
+        self.temb_group = None
+        if not self._temb_names:
+            return
+        Ls = [self.layers[n] for n in self._temb_names]
+        G = types.SimpleNamespace(names=self._temb_names, layers=Ls, g=len(Ls), cin=Ls[0].cin)
+        assert all(L.cin == G.cin and L.bias is not None for L in Ls)
+        G.offs = [0]
+        for L in Ls:
+            G.offs.append(G.offs[-1] + L.cout)
+        G.n_total = G.offs[-1]
+        assert G.n_total < 65536
+        G.bn = 160 if all(o % 160 == 0 for o in G.offs) else 64
+        G.index = {n: i for i, n in enumerate(G.names)}
+        G.w_stack = torch.cat([L.w_fwd for L in Ls], 0).contiguous()
+        G.bias = torch.cat([L.bias for L in Ls]).contiguous()
+        for i, L in enumerate(Ls):
+            L.w_fwd = G.w_stack[G.offs[i]:G.offs[i + 1]]
+        G.lora = all(L.lora is not None for L in Ls)
+        if G.lora:
+            r, g = self.r, G.g
+            lo0, op = Ls[0].lora, self.lora_opnd
+            G.a_stack = op[lo0.o_a_fwd:lo0.o_a_fwd + g * r * G.cin].view(g * r, G.cin)
+            G.sb_stack = op[lo0.o_sb_fwd:lo0.o_sb_fwd + G.n_total * r].view(G.n_total, r)
+            assert Ls[-1].lora.a_fwd.data_ptr() == G.a_stack[(g - 1) * r:].data_ptr()
+            assert Ls[-1].lora.sb_fwd.data_ptr() == G.sb_stack[G.offs[-2]:].data_ptr()
+        self.temb_group = G
+
+    def temb_all(self, st, lora):
+        """All time_emb_proj layers of one pass: out[B, sum C_i] = [st | T] @ [W ; N-ranged s*B_i]^T + b.
+        Returns (out, T): resnet i uses the column view out[:, offs[i]:offs[i+1]] as its row vector and
+        column block i of T for its LoRA weight gradients."""
+        G = self.temb_group
+        B = st.shape[0]
+        Ml = self._lrows(B)
+        srcs, bs = [ops.asrc_mat(st)], [ops.bsrc(G.w_stack)]
+        prog = [(0, 0, 0, 0, G.cin // 64, 0, 0)]
+        T = None
+        if lora and G.lora:
+            r = self.r
+            T = self._new(Ml, G.g * r)
+            ops.gemm([ops.asrc_mat(st[:Ml])], [ops.bsrc(G.a_stack)], prog, lin=True, M=Ml, N=G.g * r, out=T)
+            srcs.append(ops.asrc_mat(T))
+            bs.append(ops.bsrc(G.sb_stack))
+            prog = prog + [(1, 1, 0, 0, 1, i * r, 0, G.offs[i], G.offs[i + 1]) for i in range(G.g)]
+        out = self._new(B, G.n_total)
+        ops.gemm(srcs, bs, prog, lin=True, M=B, N=G.n_total, out=out, bias=G.bias, block_n=G.bn)
+        return out, T
 
     class _Side:
         """Run the enclosed launches on the wgrad side stream, ordered after everything enqueued so far
@@ -322,7 +382,7 @@ class UNetB200:
         out = self._new(B, Ho, Wo, N, dtype=torch.float32 if out_fp32 else BF16)
         ops.gemm(srcs, bs, prog, lin=False, M=M, N=N, geo=(Wo, Ho), out=out.view(M, N), bias=L.bias,
                  rowvec=rowvec, residual=None if residual is None else residual.reshape(M, N),
-                 round_bf16=out_fp32)
+                 round_bf16=out_fp32, dep_a_src=None if T is None else len(srcs) - 1)
         if save is not None:
             save.append(("conv3", name, xs if lbn == B else [x[:lbn] for x in xs], T, stride))
         return out
@@ -347,7 +407,8 @@ class UNetB200:
             srcs = srcs + [ops.asrc_mat(T)]   # Ml rows: tiles past them read zeros (TMA bounds)
             bs.append(ops.bsrc(L.lora.sb_fwd))
         out = self._new(M, N)
-        ops.gemm(srcs, bs, prog, lin=True, M=M, N=N, out=out, bias=L.bias, residual=residual, act=act)
+        ops.gemm(srcs, bs, prog, lin=True, M=M, N=N, out=out, bias=L.bias, residual=residual, act=act,
+                 dep_a_src=None if T is None else len(srcs) - 1)
         if save is not None:
             save.append(("linear", name, xs if Ml == M else [x[:Ml] for x in xs], T))
         return out
@@ -371,7 +432,8 @@ class UNetB200:
             bs.append(ops.bsrc(G.sb_stack))
             prog = prog + [(1, 1, 0, 0, 1, i * r, 0, i * Cc, (i + 1) * Cc) for i in range(g)]
         out = self._new(M, g * Cc)
-        ops.gemm(srcs, bs, prog, lin=True, M=M, N=g * Cc, out=out, block_n=bn)
+        ops.gemm(srcs, bs, prog, lin=True, M=M, N=g * Cc, out=out, block_n=bn,
+                 dep_a_src=None if T is None else 1)
         if save is not None:
             save.append(("lgroup", lead, x[:Ml], T))
         return [out[:, i * Cc:(i + 1) * Cc] for i in range(g)]
@@ -420,7 +482,15 @@ class UNetB200:
         cout = self.layers[p + ".conv1"].cout
         flat = [x.view(B * HW, x.shape[-1]) for x in xs]
         h = self.gn(p + ".norm1", flat, B, HW, 1e-5, True, save)
-        tproj = self.linear(p + ".time_emb_proj", [st], lora, save=save)
+        if self._temb is not None:
+            G = self.temb_group
+            i = G.index[p + ".time_emb_proj"]
+            out_all, T_all = self._temb
+            tproj = out_all[:, G.offs[i]:G.offs[i + 1]]
+            if save is not None:
+                save.append(("linear", p + ".time_emb_proj", [st[:self._lrows(st.shape[0])]], T_all, i * self.r))
+        else:
+            tproj = self.linear(p + ".time_emb_proj", [st], lora, save=save)
         h = self.conv3(p + ".conv1", [h.view(B, H, W, cin)], lora, rowvec=tproj, save=save)
         h = self.gn(p + ".norm2", [h.view(B * HW, cout)], B, HW, 1e-5, True, save)
         if cin != cout:
@@ -477,6 +547,7 @@ class UNetB200:
         ops.timestep_embed(timesteps, emb)
         hemb = self.linear("time_embedding.linear_1", [emb], False, act=1)
         st = self.linear("time_embedding.linear_2", [hemb], False, act=1)  # silu(temb)
+        self._temb = self.temb_all(st, lora) if self.temb_group is not None else None
         x = self._new(B, H, W, c0)
         Lci = self.layers["conv_in"]
         ops.conv3x3_c4(sample, Lci.w_c4, Lci.bias, x, sgn=1, round_in=True)
@@ -529,20 +600,21 @@ class UNetB200:
     # ------------------------------------------------------------------------------------
     # backward primitives
     # ------------------------------------------------------------------------------------
-    def _lora_wgrads(self, L, P_list, dy_mat, T_mat, dt_mat, taps_desc, lin, geo, M):
-        """dB += s * dy^T T ;  dA += dt^T x  (per source / tap group)."""
+    def _lora_wgrads(self, L, P_list, dy_mat, T_mat, dt_mat, taps_desc, lin, geo, M, q_c0=0):
+        """dB += s * dy^T T[:, q_c0:q_c0+r] ;  dA += dt^T x  (per source / tap group)."""
         lo = L.lora
         with UNetB200._Side(self, (dy_mat, T_mat, dt_mat, P_list)):
             ops.wgrad(ops.asrc_mat(dy_mat), ops.asrc_mat(T_mat), lo.gB, lin=True, M=M, os_row=self.r, os_col=1,
-                      alpha=self.scale)
+                      alpha=self.scale, q_c0=q_c0)
             ktot = lo.gA.shape[1]
             for (psrc, taps, offs) in P_list:
                 ops.wgrad(psrc, taps_desc(dt_mat), lo.gA, lin=lin, M=M, geo=geo, taps=taps, tap_off=offs,
                           os_row=1, os_col=ktot)
 
     def linear_bwd(self, rec, dy, need_dx=True, accumulate=None):
-        """rec = ("linear", name, xs, T).  Returns dx [M, cin_total] (or None)."""
-        _, name, xs, T = rec
+        """rec = ("linear", name, xs, T[, q_c0]).  Returns dx [M, cin_total] (or None)."""
+        _, name, xs, T = rec[:4]
+        q_c0 = rec[4] if len(rec) > 4 else 0
         L = self.layers[name]
         M = dy.shape[0]
         srcs, bs = [ops.asrc_mat(dy)], None
@@ -556,7 +628,7 @@ class UNetB200:
                 P_list.append((ops.asrc_mat(x), ((0, 0),), (coff,)))
                 coff += x.shape[1]
             self._keep.extend(xs)
-            self._lora_wgrads(L, P_list, dy, T, dt, ops.asrc_mat, True, (1, 1), M)
+            self._lora_wgrads(L, P_list, dy, T, dt, ops.asrc_mat, True, (1, 1), M, q_c0=q_c0)
         if not need_dx:
             return None
         prog = [(0, 0, 0, 0, L.cout // 64, 0, 0)]
@@ -566,7 +638,8 @@ class UNetB200:
             bs.append(ops.bsrc(L.lora.a_t))
             prog.append((1, 1, 0, 0, 1, 0, 0))
         dx = self._new(M, L.cin)
-        ops.gemm(srcs, bs, prog, lin=True, M=M, N=L.cin, out=dx, residual=accumulate)
+        ops.gemm(srcs, bs, prog, lin=True, M=M, N=L.cin, out=dx, residual=accumulate,
+                 dep_a_src=None if dt is None else 1)
         return dx
 
     def linear_group_bwd(self, rec, dpk, need_dx=True):
@@ -598,7 +671,7 @@ class UNetB200:
                 bs.append(ops.bsrc(L.lora.a_t))
                 prog.append((1, 1 + i, 0, 0, 1, i * r, 0))
         dx = self._new(M, G.cin)
-        ops.gemm(srcs, bs, prog, lin=True, M=M, N=G.cin, out=dx)
+        ops.gemm(srcs, bs, prog, lin=True, M=M, N=G.cin, out=dx, dep_a_src=None if dT is None else 1)
         return dx
 
     def conv3_bwd(self, rec, dy, need_dx=True, accumulate=None):
@@ -651,7 +724,8 @@ class UNetB200:
                 prog += [(1, 1, -dw, -dh, 1, 0, t * self.r) for t, (dw, dh) in enumerate(TAPS3)]
             dx = self._new(B, Ho, Wo, cin)
             ops.gemm(srcs, bs, prog, lin=False, M=M, N=cin, geo=geo, out=dx.view(M, cin),
-                     residual=None if accumulate is None else accumulate.reshape(M, cin))
+                     residual=None if accumulate is None else accumulate.reshape(M, cin),
+                     dep_a_src=None if dt is None else 1)
             return dx
         # stride 2: one launch per parity plane of dx
         H, W = 2 * Ho, 2 * Wo
@@ -675,7 +749,8 @@ class UNetB200:
                 plane = dx[:, p::2, q::2, :]
                 acc = None if accumulate is None else accumulate[:, p::2, q::2, :]
                 ops.gemm(srcs, bs, prog, lin=False, M=M, N=cin, geo=geo, out=plane, residual=acc,
-                         out_strides=(plane.stride(2), plane.stride(1), plane.stride(0)), epi=(Wo, Wo * Ho))
+                         out_strides=(plane.stride(2), plane.stride(1), plane.stride(0)), epi=(Wo, Wo * Ho),
+                         dep_a_src=1 if (dt is not None and p == 0 and q == 0) else None)
         return dx
 
     def gn_bwd(self, rec, dy, add=None, colsum=None):

