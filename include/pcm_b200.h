@@ -186,6 +186,15 @@ int pcm_noise_travel(const float* x, const float* noise, const float* alphas_cum
 int pcm_axpby_f64(const float* x, const float* y, const double* ca, const double* cb, int64_t per,
                   int B, double* out, void* stream);
 
+/* Flow-matching (SD3) steps, fp32 in the reference's operation order (bit-identical to its torch ops):
+ * mode 0 = PCMFMDeterministicScheduler.step (pcm_fm_deterministic_scheduler.py:226-233),
+ * mode 1 = PCMFMStochasticScheduler.step (pcm_fm_stochastic_scheduler.py:226-233, z = noise),
+ * mode 2 = scale_noise (pcm_fm_deterministic_scheduler.py:90-115).  sig / sig_next: one value per sample.
+ * (EulerSolver.euler_step / euler_style_multiphase_pred, train_pcm_lora_sd3.py:160-226, return float64
+ * like the reference and go through pcm_axpby_f64.) */
+int pcm_fm_step(const float* x, const float* v, const float* z, const float* sig, const float* sig_next,
+                int64_t per, int B, int mode, float* out, void* stream);
+
 /* ---- optimiser on the flat fp32 LoRA buffer (T15:1297-1301) ------------------------------- */
 /* out: PCM_SUMSQ_WS_DOUBLES doubles, zero-initialised once: out[0] = sum of squares; the rest is
  * scratch (block counter + per-block partials added in block order: bit-reproducible norm) */

@@ -106,6 +106,7 @@ EXPORTS = [
     "pcm_loss",
     "pcm_noise_travel",
     "pcm_axpby_f64",
+    "pcm_fm_step",
     "pcm_grad_sumsq",
     "pcm_adamw_clip",
     "pcm_ema_update",
@@ -139,6 +140,7 @@ ARGTYPES = {
     "pcm_loss": [P, P, P, P, P, L64, I, I, F, I, P, P, P, P, P],
     "pcm_noise_travel": [P, P, P, P, P, L64, I, P, P],
     "pcm_axpby_f64": [P, P, P, P, L64, I, P, P],
+    "pcm_fm_step": [P, P, P, P, P, L64, I, I, P, P],
     "pcm_grad_sumsq": [P, L64, P, P],
     "pcm_adamw_clip": [P, P, P, P, L64, P, F, F, F, F, F, F, P, I, P],
     "pcm_ema_update": [P, P, L64, F, P],

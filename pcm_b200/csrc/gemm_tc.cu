@@ -250,6 +250,8 @@ __global__ void splitk_finalize_kernel(const GemmParams p) {
   griddep_sync();
   const int nvec = (p.N + 7) >> 3;
   const long long total = static_cast<long long>(p.M) * nvec;
+  const long long slice = static_cast<long long>(p.M) * p.N;
+  const bool vec = (p.N & 7) == 0;   // 8 consecutive columns per thread: two 16-byte loads per slice
   for (long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; v < total;
        v += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int m = static_cast<int>(v / nvec);
@@ -259,20 +261,38 @@ __global__ void splitk_finalize_kernel(const GemmParams p) {
     const int h = r / p.epiW;
     const int w = r - h * p.epiW;
     const long long o = b * p.osB + h * p.osH + w * p.osW;
-    const long long slice = static_cast<long long>(p.M) * p.N;
+    float x[8];
+    const float* wp = p.ws + static_cast<long long>(m) * p.N + n;
+    if (vec) {
+      float4 a0 = *reinterpret_cast<const float4*>(wp), a1 = *reinterpret_cast<const float4*>(wp + 4);
+      for (int k = 1; k < p.ksplit; ++k) {   // split order: reproducible
+        const float4 b0 = *reinterpret_cast<const float4*>(wp + k * slice);
+        const float4 b1 = *reinterpret_cast<const float4*>(wp + k * slice + 4);
+        a0.x += b0.x; a0.y += b0.y; a0.z += b0.z; a0.w += b0.w;
+        a1.x += b1.x; a1.y += b1.y; a1.z += b1.z; a1.w += b1.w;
+      }
+      x[0] = a0.x; x[1] = a0.y; x[2] = a0.z; x[3] = a0.w;
+      x[4] = a1.x; x[5] = a1.y; x[6] = a1.z; x[7] = a1.w;
+    } else {
+      for (int e = 0; e < 8; ++e) {
+        x[e] = 0.f;
+        if (n + e < p.N) {
+          x[e] = wp[e];
+          for (int k = 1; k < p.ksplit; ++k) x[e] += wp[k * slice + e];
+        }
+      }
+    }
     for (int e = 0; e < 8 && n + e < p.N; ++e) {
-      const float* wp = p.ws + static_cast<long long>(m) * p.N + n + e;
-      float x = wp[0];
-      for (int k = 1; k < p.ksplit; ++k) x += wp[k * slice];
-      if (p.bias) x += p.bias[n + e];
-      if (p.rowvec) x += __bfloat162float(p.rowvec[b * p.rowvec_ld + n + e]);
-      if (p.residual) x += __bfloat162float(p.residual[o + n + e]);
-      if (p.act == 1) x = silu_f(x);
+      float y = x[e];
+      if (p.bias) y += p.bias[n + e];
+      if (p.rowvec) y += __bfloat162float(p.rowvec[b * p.rowvec_ld + n + e]);
+      if (p.residual) y += __bfloat162float(p.residual[o + n + e]);
+      if (p.act == 1) y = silu_f(y);
       if (p.out_fp32) {
-        if (p.round_bf16) x = __bfloat162float(__float2bfloat16_rn(x));
-        reinterpret_cast<float*>(p.out)[o + n + e] = x;
+        if (p.round_bf16) y = __bfloat162float(__float2bfloat16_rn(y));
+        reinterpret_cast<float*>(p.out)[o + n + e] = y;
       } else {
-        reinterpret_cast<bf16*>(p.out)[o + n + e] = __float2bfloat16_rn(x);
+        reinterpret_cast<bf16*>(p.out)[o + n + e] = __float2bfloat16_rn(y);
       }
     }
   }
@@ -467,8 +487,8 @@ static int encode_asrc(CUtensorMap* map, const pcm_asrc& a, int lin, int geoW, i
 static bool epi2_enabled() {
   static int e = -1;
   if (e < 0) {
-    const char* s = getenv("PCM_EPI_V2");
-    e = (s != nullptr && s[0] == '1') ? 1 : 0;
+    const char* s = getenv("PCM_EPI_V2");   // default on; PCM_EPI_V2=0 keeps the two-phase v1 epilogue
+    e = (s != nullptr && s[0] == '0') ? 0 : 1;
   }
   return e == 1;
 }
@@ -565,7 +585,7 @@ static int launch_gemm(const pcm_gemm_desc* d, cudaStream_t stream) {
   p.tiles_n = (d->N + d->block_n - 1) / d->block_n;
   p.num_kblocks = nkb;
   const int stage_bytes = kATileBytes + d->block_n * 128;
-  // epilogue v2 (opt-in, PCM_EPI_V2=1): bf16 output, no activation, short K programs (the
+  // epilogue v2 (default; PCM_EPI_V2=0 disables): bf16 output, no activation, short K programs (the
   // epilogue-bound layers; it needs 64 KB of boxes, which the long-K convolutions rather spend on
   // pipeline stages), row mapping expressible as 32-row TMA boxes
   bool epi2 = epi2_enabled() && !d->out_fp32 && d->act == 0 && d->N >= 32 && (d->N % 8) == 0 && nkb <= 24 &&

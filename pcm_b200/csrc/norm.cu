@@ -140,19 +140,27 @@ __global__ void __launch_bounds__(512, 2) gn_stats_kernel(const bf16* __restrict
   __syncthreads();
   const int cpg = C / G;
   const float n = static_cast<float>(p1 - p0);   // pixels per channel in this block
+  const float inv_n = 1.f / n;
+  // per channel: (mean, M2) from the pivot-shifted sums, all threads (no divisions in the loops)
+  for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
+    const float s = s_sum[ch];
+    const float m2 = s_sq[ch] - s * s * inv_n;
+    s_sum[ch] = s_piv[ch] + s * inv_n;
+    s_sq[ch] = m2;
+  }
+  __syncthreads();
+  // per group: Chan merge of its channels (equal counts)
+  const float inv_cpg = 1.f / static_cast<float>(cpg);
   for (int g = threadIdx.x; g < G; g += blockDim.x) {
     float msum = 0.f, m2 = 0.f;
     for (int i = 0; i < cpg; ++i) {
-      const int ch = g * cpg + i;
-      const float s = s_sum[ch];
-      msum += s_piv[ch] + s / n;
-      m2 += s_sq[ch] - s * s / n;
+      msum += s_sum[g * cpg + i];
+      m2 += s_sq[g * cpg + i];
     }
-    const float mg = msum / cpg;
+    const float mg = msum * inv_cpg;
     float dev = 0.f;
     for (int i = 0; i < cpg; ++i) {
-      const int ch = g * cpg + i;
-      const float d = s_piv[ch] + s_sum[ch] / n - mg;
+      const float d = s_sum[g * cpg + i] - mg;
       dev += d * d;
     }
     float* o = part + (static_cast<long long>(b * nblk + blockIdx.x) * G + g) * 2;
