@@ -400,6 +400,8 @@ def main():
         }
         print(json.dumps(line), flush=True)
     if world > 1:
+        step.graph = step.graph_opt = None      # graphs first, then the communicator
+        torch.cuda.synchronize()
         dist.destroy_process_group()
 
 

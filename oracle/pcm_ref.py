@@ -128,6 +128,12 @@ def pcm_step_ref(cfg, params, batch, *, multiphase, num_ddim=50, loss_type="hube
     latents, noise = rq(batch["latents"]), rq(batch["noise"])                 # T15:1136, 1139
     index, w = batch["index"], batch["w"]
     prompt, uncond = batch["prompt_embeds"], batch["uncond_prompt_embeds"]
+    # SDXL (train_pcm_lora_sdxl_adv.py:1094-1133, 1215-1221): added_cond_kwargs; the unconditional
+    # teacher pass uses ZERO pooled text embeddings and the same time ids
+    addc = addu = None
+    if "text_embeds" in batch:
+        addc = dict(text_embeds=rq(batch["text_embeds"]), time_ids=batch["time_ids"])
+        addu = dict(text_embeds=torch.zeros_like(batch["text_embeds"]), time_ids=batch["time_ids"])
     topk = 1000 // num_ddim                                                   # T15:1143-1146
     start_t = solver.ddim_timesteps[index]                                    # T15:1151
     t = torch.clamp(start_t - topk, min=0)                                    # T15:1152-1155
@@ -140,16 +146,16 @@ def pcm_step_ref(cfg, params, batch, *, multiphase, num_ddim=50, loss_type="hube
         noisy = add_noise(ac, latents, noise, start_t)                        # T15:1178
     w4 = rq(w.reshape(-1, 1, 1, 1))                                           # T15:1183-1185
 
-    eps = student(noisy, start_t, prompt)                                     # T15:1192-1198
+    eps = student(noisy, start_t, prompt, addc)                               # T15:1192-1198
     x0 = predicted_origin(eps, start_t, noisy, prediction_type, alpha_schedule, sigma_schedule)
     model_pred, end_t = solver.ddim_style_multiphase_pred(x0, eps, index, multiphase)  # T15:1209
     model_pred = c_skip_s * noisy + c_out_s * model_pred                      # T15:1212
 
     with torch.no_grad():                                                     # T15:1217-1258
-        eps_c = teacher(noisy, start_t, prompt)
+        eps_c = teacher(noisy, start_t, prompt, addc)
         x0_c = predicted_origin(eps_c, start_t, noisy, prediction_type, alpha_schedule, sigma_schedule)
         if apply_cfg_solver:
-            eps_u = teacher(noisy, start_t, uncond)
+            eps_u = teacher(noisy, start_t, uncond, addu)
             x0_u = predicted_origin(eps_u, start_t, noisy, prediction_type, alpha_schedule, sigma_schedule)
         else:
             eps_u, x0_u = eps_c, x0_c
@@ -157,7 +163,7 @@ def pcm_step_ref(cfg, params, batch, *, multiphase, num_ddim=50, loss_type="hube
         pred_noise = eps_c + w4 * (eps_c - eps_u)                             # T15:1255-1257
         x_prev = solver.ddim_step(pred_x0, pred_noise, index)                 # T15:1258 (float64)
 
-        eps_t = student(x_prev.float(), t, prompt)                            # T15:1263-1268
+        eps_t = student(x_prev.float(), t, prompt, addc)                      # T15:1263-1268
         x0_t = predicted_origin(eps_t, t, x_prev, prediction_type, alpha_schedule, sigma_schedule)
         target, end_t2 = solver.ddim_style_multiphase_pred(x0_t, eps_t, index, multiphase)
         target = c_skip * x_prev + c_out * target                             # T15:1280
@@ -196,7 +202,7 @@ def clip_and_adamw_ref(params, grads, state, *, lr, betas=(0.9, 0.999), eps=1e-8
     return total
 
 
-def make_batch(cfg, B, hw, seed=0, num_ddim=50, w_min=4.0, w_max=5.0, index=None):
+def make_batch(cfg, B, hw, seed=0, num_ddim=50, w_min=4.0, w_max=5.0, index=None, zero_uncond=False):
     """Synthetic inputs of SURVEY.md section 8(d): CPU generator, fixed seeds per tensor."""
     def g(s):
         return torch.Generator().manual_seed(seed * 1000 + s)
@@ -207,5 +213,12 @@ def make_batch(cfg, B, hw, seed=0, num_ddim=50, w_min=4.0, w_max=5.0, index=None
     if index is None:
         index = torch.randint(0, num_ddim, (B,), generator=g(4))
     w = (w_max - w_min) * torch.rand(B, generator=g(5)) + w_min
-    return dict(latents=latents, noise=noise, prompt_embeds=prompt, uncond_prompt_embeds=uncond,
-                index=index.long(), w=w)
+    out = dict(latents=latents, noise=noise, prompt_embeds=prompt, uncond_prompt_embeds=uncond,
+               index=index.long(), w=w)
+    if getattr(cfg, "addition_embed", False):   # SDXL: pooled text embedding + (orig size, crop, target size)
+        out["text_embeds"] = torch.randn(B, cfg.text_embed_dim, generator=g(6))
+        res = float(hw * 8)
+        out["time_ids"] = torch.tensor([[res, res, 0.0, 0.0, res, res]] * B).long()
+        if zero_uncond:
+            out["uncond_prompt_embeds"] = torch.zeros_like(uncond)          # TXL:1215-1218
+    return out

@@ -44,6 +44,25 @@ class UNetConfig:
     down_attn: Tuple[bool, ...] = (True, True, True, False)
     lora_rank: int = 64
     lora_alpha: float = 8.0       # peft LoraConfig default
+    # SDXL-style extensions (diffusers config of stabilityai/stable-diffusion-xl-base-1.0; call sites
+    # train_pcm_lora_sdxl_adv.py:1094-1133 added_cond_kwargs, :1215-1221 zero uncond embeddings)
+    transformer_layers_per_block: Tuple[int, ...] = ()      # () -> 1 everywhere
+    heads_per_block: Tuple[int, ...] = ()                   # () -> num_heads everywhere
+    use_linear_projection: bool = False
+    addition_embed: bool = False                            # addition_embed_type == "text_time"
+    addition_time_embed_dim: int = 256
+    text_embed_dim: int = 1280
+    num_time_ids: int = 6
+
+    def depth(self, level):
+        return self.transformer_layers_per_block[level] if self.transformer_layers_per_block else 1
+
+    def heads(self, level):
+        return self.heads_per_block[level] if self.heads_per_block else self.num_heads
+
+    @property
+    def add_embed_in(self):
+        return self.text_embed_dim + self.num_time_ids * self.addition_time_embed_dim
 
     @property
     def time_embed_dim(self):
@@ -57,6 +76,13 @@ class UNetConfig:
 SD15 = UNetConfig()
 TINY = UNetConfig(block_out_channels=(64, 128, 128, 128), cross_attention_dim=64, num_heads=2,
                   lora_rank=64)
+SDXL = UNetConfig(block_out_channels=(320, 640, 1280), down_attn=(False, True, True),
+                  transformer_layers_per_block=(1, 2, 10), heads_per_block=(5, 10, 20),
+                  cross_attention_dim=2048, use_linear_projection=True, addition_embed=True)
+TINY_XL = UNetConfig(block_out_channels=(64, 128, 128), down_attn=(False, True, True),
+                     transformer_layers_per_block=(1, 2, 3), heads_per_block=(1, 2, 2),
+                     cross_attention_dim=128, use_linear_projection=True, addition_embed=True,
+                     addition_time_embed_dim=64, text_embed_dim=128)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -81,38 +107,44 @@ def layer_table(cfg: UNetConfig):
         if cin != cout:
             L.append((p + ".conv_shortcut", "conv", cin, cout, 1))
 
-    def transformer(p, c):
+    def transformer(p, c, depth):
+        # use_linear_projection: proj_in / proj_out are nn.Linear (SDXL), else 1x1 convolutions (SD1.5)
+        kind, k = ("linear", 0) if cfg.use_linear_projection else ("conv", 1)
         L.append((p + ".norm", "gn", c, c, 0))
-        L.append((p + ".proj_in", "conv", c, c, 1))
-        t = p + ".transformer_blocks.0"
-        L.append((t + ".norm1", "ln", c, c, 0))
-        for n in ("to_q", "to_k", "to_v"):
-            L.append((t + ".attn1." + n, "linear_nobias", c, c, 0))
-        L.append((t + ".attn1.to_out.0", "linear", c, c, 0))
-        L.append((t + ".norm2", "ln", c, c, 0))
-        L.append((t + ".attn2.to_q", "linear_nobias", c, c, 0))
-        L.append((t + ".attn2.to_k", "linear_nobias", cfg.cross_attention_dim, c, 0))
-        L.append((t + ".attn2.to_v", "linear_nobias", cfg.cross_attention_dim, c, 0))
-        L.append((t + ".attn2.to_out.0", "linear", c, c, 0))
-        L.append((t + ".norm3", "ln", c, c, 0))
-        L.append((t + ".ff.net.0.proj", "linear", c, 8 * c, 0))
-        L.append((t + ".ff.net.2", "linear", 4 * c, c, 0))
-        L.append((p + ".proj_out", "conv", c, c, 1))
+        L.append((p + ".proj_in", kind, c, c, k))
+        for d in range(depth):
+            t = p + f".transformer_blocks.{d}"
+            L.append((t + ".norm1", "ln", c, c, 0))
+            for n in ("to_q", "to_k", "to_v"):
+                L.append((t + ".attn1." + n, "linear_nobias", c, c, 0))
+            L.append((t + ".attn1.to_out.0", "linear", c, c, 0))
+            L.append((t + ".norm2", "ln", c, c, 0))
+            L.append((t + ".attn2.to_q", "linear_nobias", c, c, 0))
+            L.append((t + ".attn2.to_k", "linear_nobias", cfg.cross_attention_dim, c, 0))
+            L.append((t + ".attn2.to_v", "linear_nobias", cfg.cross_attention_dim, c, 0))
+            L.append((t + ".attn2.to_out.0", "linear", c, c, 0))
+            L.append((t + ".norm3", "ln", c, c, 0))
+            L.append((t + ".ff.net.0.proj", "linear", c, 8 * c, 0))
+            L.append((t + ".ff.net.2", "linear", 4 * c, c, 0))
+        L.append((p + ".proj_out", kind, c, c, k))
 
     L.append(("conv_in", "conv", cfg.in_channels, ch[0], 3))
     L.append(("time_embedding.linear_1", "linear", ch[0], temb, 0))
     L.append(("time_embedding.linear_2", "linear", temb, temb, 0))
+    if cfg.addition_embed:
+        L.append(("add_embedding.linear_1", "linear", cfg.add_embed_in, temb, 0))
+        L.append(("add_embedding.linear_2", "linear", temb, temb, 0))
     cin = ch[0]
     for i, cout in enumerate(ch):
         for j in range(cfg.layers_per_block):
             resnet(f"down_blocks.{i}.resnets.{j}", cin, cout)
             if cfg.down_attn[i]:
-                transformer(f"down_blocks.{i}.attentions.{j}", cout)
+                transformer(f"down_blocks.{i}.attentions.{j}", cout, cfg.depth(i))
             cin = cout
         if i < len(ch) - 1:
             L.append((f"down_blocks.{i}.downsamplers.0.conv", "conv", cout, cout, 3))
     resnet("mid_block.resnets.0", ch[-1], ch[-1])
-    transformer("mid_block.attentions.0", ch[-1])
+    transformer("mid_block.attentions.0", ch[-1], cfg.depth(len(ch) - 1))
     resnet("mid_block.resnets.1", ch[-1], ch[-1])
     rev = list(reversed(ch))
     prev = rev[0]
@@ -123,7 +155,7 @@ def layer_table(cfg: UNetConfig):
             rin = prev if j == 0 else cout
             resnet(f"up_blocks.{i}.resnets.{j}", rin + skip, cout)
             if cfg.up_attn[i]:
-                transformer(f"up_blocks.{i}.attentions.{j}", cout)
+                transformer(f"up_blocks.{i}.attentions.{j}", cout, cfg.depth(len(ch) - 1 - i))
         if i < len(ch) - 1:
             L.append((f"up_blocks.{i}.upsamplers.0.conv", "conv", cout, cout, 3))
         prev = cout
@@ -228,9 +260,9 @@ class UNetRef:
     def ln(self, name, x):
         return _q(F.layer_norm(x, (x.shape[-1],), self.P[name + ".weight"], self.P[name + ".bias"], 1e-5), self.emu)
 
-    def attention(self, q, k, v):
+    def attention(self, q, k, v, H=None):
         B, S, Cc = q.shape
-        H = self.cfg.num_heads
+        H = H or self.cfg.num_heads
         d = Cc // H
         q = q.view(B, S, H, d).transpose(1, 2)
         k = k.view(B, k.shape[1], H, d).transpose(1, 2)
@@ -255,47 +287,71 @@ class UNetRef:
         sc = self.conv(p + ".conv_shortcut", x) if cin != cout else x
         return self.conv(p + ".conv2", h, extra=sc)
 
-    def transformer(self, p, x, ctx):
+    def transformer(self, p, x, ctx, level=0):
+        """Transformer2DModel: GN -> proj_in -> depth x BasicTransformerBlock -> proj_out -> + residual.
+        use_linear_projection (SDXL): proj_in / proj_out are nn.Linear applied to [B, HW, C] tokens;
+        otherwise 1x1 convolutions on NCHW (SD1.5) - the same contraction."""
         B, Cc, Hh, Ww = x.shape
+        H = self.cfg.heads(level)
         r = x
         h = self.gn(p + ".norm", x, 1e-6, False)
-        h = self.conv(p + ".proj_in", h)
-        h = h.permute(0, 2, 3, 1).reshape(B, Hh * Ww, Cc)
-        t = p + ".transformer_blocks.0"
-        n = self.ln(t + ".norm1", h)
-        a = self.attention(self.linear(t + ".attn1.to_q", n), self.linear(t + ".attn1.to_k", n),
-                           self.linear(t + ".attn1.to_v", n))
-        h = self.linear(t + ".attn1.to_out.0", a, extra=h)
-        n = self.ln(t + ".norm2", h)
-        a = self.attention(self.linear(t + ".attn2.to_q", n), self.linear(t + ".attn2.to_k", ctx),
-                           self.linear(t + ".attn2.to_v", ctx))
-        h = self.linear(t + ".attn2.to_out.0", a, extra=h)
-        n = self.ln(t + ".norm3", h)
-        u = self.linear(t + ".ff.net.0.proj", n)
-        a_, g_ = u.chunk(2, dim=-1)
-        gg = _q(a_ * F.gelu(g_), self.emu)                                   # GEGLU, exact-erf GELU
-        h = self.linear(t + ".ff.net.2", gg, extra=h)
+        if self.cfg.use_linear_projection:
+            h = h.permute(0, 2, 3, 1).reshape(B, Hh * Ww, Cc)
+            h = self.linear(p + ".proj_in", h)
+        else:
+            h = self.conv(p + ".proj_in", h)
+            h = h.permute(0, 2, 3, 1).reshape(B, Hh * Ww, Cc)
+        for d in range(self.cfg.depth(level)):
+            t = p + f".transformer_blocks.{d}"
+            n = self.ln(t + ".norm1", h)
+            a = self.attention(self.linear(t + ".attn1.to_q", n), self.linear(t + ".attn1.to_k", n),
+                               self.linear(t + ".attn1.to_v", n), H)
+            h = self.linear(t + ".attn1.to_out.0", a, extra=h)
+            n = self.ln(t + ".norm2", h)
+            a = self.attention(self.linear(t + ".attn2.to_q", n), self.linear(t + ".attn2.to_k", ctx),
+                               self.linear(t + ".attn2.to_v", ctx), H)
+            h = self.linear(t + ".attn2.to_out.0", a, extra=h)
+            n = self.ln(t + ".norm3", h)
+            u = self.linear(t + ".ff.net.0.proj", n)
+            a_, g_ = u.chunk(2, dim=-1)
+            gg = _q(a_ * F.gelu(g_), self.emu)                               # GEGLU, exact-erf GELU
+            h = self.linear(t + ".ff.net.2", gg, extra=h)
+        if self.cfg.use_linear_projection:
+            h = self.linear(p + ".proj_out", h, extra=r.permute(0, 2, 3, 1).reshape(B, Hh * Ww, Cc))
+            return h.reshape(B, Hh, Ww, Cc).permute(0, 3, 1, 2)
         h = h.reshape(B, Hh, Ww, Cc).permute(0, 3, 1, 2)
         return self.conv(p + ".proj_out", h, extra=r)
 
-    def time_embed(self, timesteps):
-        c0 = self.cfg.block_out_channels[0]
-        half = c0 // 2
+    def _sinusoid(self, values, dim):
+        half = dim // 2
         f = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32) / half)
-        e = timesteps[:, None].float() * f[None]
-        emb = torch.cat([torch.cos(e), torch.sin(e)], dim=-1)                # flip_sin_to_cos
-        emb = _q(emb, self.emu)
-        h = self.linear("time_embedding.linear_1", emb, act="silu")
-        # every consumer applies SiLU to temb first (ResnetBlock2D), so SiLU is folded in here
-        return self.linear("time_embedding.linear_2", h, act="silu")
+        e = values[:, None].float() * f[None]
+        return torch.cat([torch.cos(e), torch.sin(e)], dim=-1)               # flip_sin_to_cos, shift 0
 
-    def __call__(self, sample, timesteps, encoder_hidden_states):
-        """sample [B,4,H,W], timesteps [B] int64, encoder_hidden_states [B,77,D] -> eps [B,4,H,W]"""
+    def time_embed(self, timesteps, added_cond_kwargs=None):
+        c0 = self.cfg.block_out_channels[0]
+        emb = _q(self._sinusoid(timesteps, c0), self.emu)
+        h = self.linear("time_embedding.linear_1", emb, act="silu")
+        if not self.cfg.addition_embed:
+            # every consumer applies SiLU to temb first (ResnetBlock2D), so SiLU is folded in here
+            return self.linear("time_embedding.linear_2", h, act="silu")
+        # SDXL "text_time": emb = time_embedding(t) + add_embedding(cat[text_embeds, sinusoid(time_ids)])
+        temb = self.linear("time_embedding.linear_2", h)
+        text_embeds, time_ids = added_cond_kwargs["text_embeds"], added_cond_kwargs["time_ids"]
+        B = time_ids.shape[0]
+        tid = self._sinusoid(time_ids.flatten(), self.cfg.addition_time_embed_dim).reshape(B, -1)
+        add = _q(torch.cat([text_embeds.float(), tid], dim=-1), self.emu)
+        a = self.linear("add_embedding.linear_1", add, act="silu")
+        return self.linear("add_embedding.linear_2", a, extra=temb, act="silu")
+
+    def __call__(self, sample, timesteps, encoder_hidden_states, added_cond_kwargs=None):
+        """sample [B,4,H,W], timesteps [B] int64, encoder_hidden_states [B,77,D] -> eps [B,4,H,W]
+        added_cond_kwargs (SDXL): {"text_embeds" [B, 1280], "time_ids" [B, 6]}"""
         cfg = self.cfg
         dt = self.P["conv_in.weight"].dtype
         x = _q(sample.to(dt), self.emu)
         ctx = _q(encoder_hidden_states.to(dt), self.emu)
-        st = self.time_embed(timesteps)
+        st = self.time_embed(timesteps, added_cond_kwargs)
         x = self.conv("conv_in", x)
         skips = [x]
         nb = len(cfg.block_out_channels)
@@ -303,13 +359,13 @@ class UNetRef:
             for j in range(cfg.layers_per_block):
                 x = self.resnet(f"down_blocks.{i}.resnets.{j}", x, st)
                 if cfg.down_attn[i]:
-                    x = self.transformer(f"down_blocks.{i}.attentions.{j}", x, ctx)
+                    x = self.transformer(f"down_blocks.{i}.attentions.{j}", x, ctx, i)
                 skips.append(x)
             if i < nb - 1:
                 x = self.conv(f"down_blocks.{i}.downsamplers.0.conv", x, stride=2)
                 skips.append(x)
         x = self.resnet("mid_block.resnets.0", x, st)
-        x = self.transformer("mid_block.attentions.0", x, ctx)
+        x = self.transformer("mid_block.attentions.0", x, ctx, nb - 1)
         x = self.resnet("mid_block.resnets.1", x, st)
         self.taps["mid"] = x
         for i in range(nb):
@@ -317,7 +373,7 @@ class UNetRef:
                 x = torch.cat([x, skips.pop()], dim=1)
                 x = self.resnet(f"up_blocks.{i}.resnets.{j}", x, st)
                 if cfg.up_attn[i]:
-                    x = self.transformer(f"up_blocks.{i}.attentions.{j}", x, ctx)
+                    x = self.transformer(f"up_blocks.{i}.attentions.{j}", x, ctx, nb - 1 - i)
             if i < nb - 1:
                 x = F.interpolate(x, scale_factor=2.0, mode="nearest")
                 x = self.conv(f"up_blocks.{i}.upsamplers.0.conv", x)

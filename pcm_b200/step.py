@@ -94,6 +94,13 @@ class PCMTrainStep:
         self.noisy3 = torch.zeros(3 * B, height, width, 4, **f32)
         self.noisy = self.noisy3[:B]
         self.start_t3 = torch.zeros(3 * B, **i64)
+        # SDXL added_cond_kwargs (train_pcm_lora_sdxl_adv.py:1094-1133): pooled text embedding + time ids,
+        # laid out like ctx3 = [prompt; prompt; uncond]; the unconditional rows keep ZERO text embeddings
+        # (uncond_pooled_prompt_embeds, :1215-1221) and the same time ids
+        self.addc = cfg.addition_embed
+        if self.addc:
+            self.in_text3 = torch.zeros(3 * B, cfg.text_embed_dim, device=device, dtype=BF16)
+            self.in_time_ids3 = torch.zeros(3 * B, cfg.num_time_ids, **i64)
         self.merged = os.environ.get("PCM_MERGE_PASSES", "1") != "0"
         # data parallel: overlap the gradient all-reduce with the backward pass (PCM_DP_OVERLAP=0: one
         # flat all-reduce after the backward)
@@ -120,25 +127,29 @@ class PCMTrainStep:
             self.start_t3[i * B:(i + 1) * B].copy_(self.start_t)
         self.start_t3[:B].copy_(self.start_t)
         self.in_ctx3[B * 77:2 * B * 77].copy_(self.in_prompt)
+
+        def added(lo, hi):
+            return (self.in_text3[lo:hi], self.in_time_ids3[lo:hi]) if self.addc else None
         if self.merged:
             # one pass: [student | teacher cond | teacher uncond]; LoRA only on the student samples
             eps_all = u.forward(self.noisy3[:nb * B], self.start_t3[:nb * B],
                                 self.in_ctx3 if nb == 3 else self.in_ctx3[:2 * B * 77],
-                                lora=True, save=True, lora_batch=B)
+                                lora=True, save=True, lora_batch=B, added_cond=added(0, nb * B))
             eps_s, eps_c = eps_all[:B], eps_all[B:2 * B]
             eps_u = eps_all[2 * B:] if nb == 3 else eps_c
         else:
-            eps_s = u.forward(self.noisy, self.start_t, self.in_prompt, lora=True, save=True)
+            eps_s = u.forward(self.noisy, self.start_t, self.in_prompt, lora=True, save=True, added_cond=added(0, B))
             if self.apply_cfg:
-                eps_cu = u.forward(self.noisy3[B:], self.start_t3[B:], self.in_ctx3[B * 77:], lora=False)
+                eps_cu = u.forward(self.noisy3[B:], self.start_t3[B:], self.in_ctx3[B * 77:], lora=False,
+                                   added_cond=added(B, 3 * B))
                 eps_c, eps_u = eps_cu[:B], eps_cu[B:]
             else:
-                eps_c = u.forward(self.noisy, self.start_t, self.in_prompt, lora=False)
+                eps_c = u.forward(self.noisy, self.start_t, self.in_prompt, lora=False, added_cond=added(0, B))
                 eps_u = eps_c
         self.teacher_step_kernel(eps_c, eps_u)
         if self.ema_master is not None:      # opt-in EMA target: same network, EMA LoRA factors
             u.refresh_lora(self.ema_master)
-        eps_t = u.forward(self.x_prev, self.t, self.in_prompt, lora=True)
+        eps_t = u.forward(self.x_prev, self.t, self.in_prompt, lora=True, added_cond=added(0, B))
         if self.ema_master is not None:
             u.refresh_lora()
         self.loss_kernel(eps_s, eps_t)
@@ -203,10 +214,13 @@ class PCMTrainStep:
         torch.cuda.synchronize()
         self.graph, self.graph_opt = None, None
         n0 = ops.LAUNCHES["count"]
-        in_graph = self.world == 1 or os.environ.get("PCM_NCCL_IN_GRAPH", "1") == "1"
+        in_graph = self.world == 1 or os.environ.get("PCM_NCCL_IN_GRAPH", "0") == "1"
         if in_graph:
-            # ONE graph for the whole iteration; data parallel: the bucketed NCCL all-reduces are
-            # captured on their side streams inside it (PCM_NCCL_IN_GRAPH=0 keeps them eager)
+            # ONE graph for the whole iteration.  Data parallel default: graph(forward + backward) ->
+            # eager NCCL all-reduce -> graph(optimiser).  PCM_NCCL_IN_GRAPH=1 (experimental) captures the
+            # bucketed, backward-overlapped all-reduces inside the single graph: it steps correctly on 2
+            # GPUs (measured 78.6 vs 78.5 ms/step) but process-group teardown hung while the graph was
+            # alive, so it is not the default; drop `self.graph` before destroy_process_group().
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 self.run_eager()
@@ -234,8 +248,18 @@ class PCMTrainStep:
         self.unet.refresh_lora()
         return self.graph
 
-    def load_inputs(self, latents, noise, index, w, prompt, uncond, non_blocking=True):
-        """Copy one batch into the static slots (host pinned or device tensors, NHWC latents)."""
+    def load_inputs(self, latents, noise, index, w, prompt, uncond, text_embeds=None, time_ids=None,
+                    non_blocking=True):
+        """Copy one batch into the static slots (host pinned or device tensors, NHWC latents).
+        text_embeds [B, text_embed_dim] / time_ids [B, 6]: SDXL added conditions."""
+        if self.addc:
+            if text_embeds is None or time_ids is None:
+                raise ValueError("this UNet needs text_embeds and time_ids (added_cond_kwargs)")
+            B = self.B
+            self.in_text3[:B].copy_(text_embeds, non_blocking=non_blocking)
+            self.in_text3[B:2 * B].copy_(text_embeds, non_blocking=non_blocking)
+            for i in range(3):
+                self.in_time_ids3[i * B:(i + 1) * B].copy_(time_ids, non_blocking=non_blocking)
         self.in_latents.copy_(latents, non_blocking=non_blocking)
         self.in_noise.copy_(noise, non_blocking=non_blocking)
         self.in_index.copy_(index, non_blocking=non_blocking)

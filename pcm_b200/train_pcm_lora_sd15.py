@@ -32,8 +32,10 @@ from . import config, dp, lr_schedules, weights
 from .step import PCMTrainStep
 
 
-def parse_args(argv=None):
-    p = argparse.ArgumentParser(description="PCM-LoRA distillation (SD1.5) on B200")
+def parse_args(argv=None, extra=None):
+    p = argparse.ArgumentParser(description="PCM-LoRA distillation on B200")
+    if extra is not None:
+        extra(p)
     # ---- flags of the reference script, verbatim names / defaults ----
     p.add_argument("--pretrained_teacher_model", type=str, default=None,
                    help="directory with unet/diffusion_pytorch_model.safetensors; omitted -> seeded random init")
@@ -181,7 +183,9 @@ def main(args):
         pg = dp.init_process_group("nccl", dev)
     if args.seed is not None:
         torch.manual_seed(dp.rank_seed(args.seed, rank))        # set_seed(args.seed + process_index)
-    cfg = config.UNetConfig(lora_rank=args.lora_rank) if not getattr(args, "_cfg", None) else args._cfg
+    import dataclasses
+    cfg = getattr(args, "_cfg", None) or dataclasses.replace(getattr(args, "_base_cfg", config.SD15),
+                                                               lora_rank=args.lora_rank)
     if args.pretrained_teacher_model:
         from safetensors.torch import load_file
         sd = load_file(os.path.join(args.pretrained_teacher_model, "unet", "diffusion_pytorch_model.safetensors"))
@@ -206,6 +210,9 @@ def main(args):
     uncond = None
     if args.uncond_embeds:
         uncond = torch.load(args.uncond_embeds).float().reshape(-1, 77, cfg.cross_attention_dim)
+    elif cfg.addition_embed:
+        # SDXL: zero unconditional embeddings (train_pcm_lora_sdxl_adv.py:1215-1221)
+        uncond = torch.zeros(1, 77, cfg.cross_attention_dim)
     elif args.synthetic:
         # synthetic stand-in for text_encoder([""] * B): one embedding repeated over the batch
         uncond = torch.randn(1, 77, cfg.cross_attention_dim, generator=torch.Generator().manual_seed(3))
@@ -223,6 +230,7 @@ def main(args):
         args.max_train_steps = args.num_train_epochs * steps_per_epoch
 
     def next_batch(i):
+        extra = ()
         if files:
             d = torch.load(files[(i * world + rank) % len(files)])
             lat, pe = d["latents"].float(), d["prompt_embeds"].float()
@@ -232,17 +240,23 @@ def main(args):
                     "the CFG-augmented solver needs the CLIP encoding of the empty prompt (T15:1053-1059, "
                     "1237-1258): put `uncond_prompt_embeds` into the cache files or pass --uncond_embeds")
             unc = unc.float().reshape(-1, 77, cfg.cross_attention_dim)
+            if cfg.addition_embed:
+                extra = (d["text_embeds"].bfloat16(), d["time_ids"].long())
         else:
             lat = torch.randn(B, 4, hw, hw, generator=gen)
             pe = torch.randn(B, 77, cfg.cross_attention_dim, generator=gen)
             unc = uncond
+            if cfg.addition_embed:   # pooled text embedding + (original size, crop top-left, target size)
+                res = args.resolution
+                extra = (torch.randn(B, cfg.text_embed_dim, generator=gen).bfloat16(),
+                         torch.tensor([[res, res, 0, 0, res, res]] * B))
         if unc.shape[0] == 1:
             unc = unc.repeat(B, 1, 1)
         noise = torch.randn(B, 4, hw, hw, generator=gen)
         index = torch.randint(0, args.num_ddim_timesteps, (B,), generator=gen)
         w = (args.w_max - args.w_min) * torch.rand(B, generator=gen) + args.w_min
         nhwc = lambda x: x.permute(0, 2, 3, 1).contiguous()
-        return nhwc(lat), nhwc(noise), index, w, pe.bfloat16(), unc.bfloat16()
+        return (nhwc(lat), nhwc(noise), index, w, pe.bfloat16(), unc.bfloat16()) + tuple(extra)
 
     os.makedirs(args.output_dir, exist_ok=True)
     global_step = 0

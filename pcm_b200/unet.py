@@ -74,7 +74,8 @@ class UNetB200:
                         L.w_t = W.permute(1, 2, 3, 0).reshape(cin, -1).contiguous().to(device=device, dtype=BF16)
             else:
                 L.w_fwd = W.contiguous().to(device=device, dtype=BF16)
-                if need_backward and not name.endswith(no_dgrad) and not name.startswith("time_embedding"):
+                if need_backward and not name.endswith(no_dgrad) and \
+                        not name.startswith(("time_embedding", "add_embedding")):
                     L.w_t = W.t().contiguous().to(device=device, dtype=BF16)
             if lora and is_lora_target(name):
                 taps = k * k if kind == "conv" else 1
@@ -460,15 +461,15 @@ class UNetB200:
             save.append(("ln", name, x[:Ml], stats[:Ml]))
         return out
 
-    def attention(self, q, k, v, B, Sq, Skv, save=None):
-        Hh = self.cfg.num_heads
+    def attention(self, q, k, v, B, Sq, Skv, save=None, heads=None):
+        Hh = heads or self.cfg.num_heads
         D = q.shape[1] // Hh
         out = self._new(q.shape[0], q.shape[1])
         lse = self._new(B, Hh, Sq, dtype=torch.float32)
         ops.attn_fwd(q, k, v, out, lse, B, Hh, Sq, Skv, D, D ** -0.5)
         if save is not None:
             lb = self._lrows(B)
-            save.append(("attn", q[:lb * Sq], k[:lb * Skv], v[:lb * Skv], out[:lb * Sq], lse[:lb], lb, Sq, Skv))
+            save.append(("attn", q[:lb * Sq], k[:lb * Skv], v[:lb * Skv], out[:lb * Sq], lse[:lb], lb, Sq, Skv, Hh))
         return out
 
     # ------------------------------------------------------------------------------------
@@ -499,29 +500,44 @@ class UNetB200:
             sc = xs[0]
         return self.conv3(p + ".conv2", [h.view(B, H, W, cout)], lora, residual=sc, save=save)
 
+    def _level_of(self, name):
+        """Resolution level of a block name (selects transformer depth and head count)."""
+        nb = len(self.cfg.block_out_channels)
+        parts = name.split(".")
+        if parts[0] == "mid_block":
+            return nb - 1
+        i = int(parts[1])
+        return i if parts[0] == "down_blocks" else nb - 1 - i
+
     def transformer(self, p, x, ctx, lora, save):
+        """Transformer2DModel: GN -> proj_in -> depth x BasicTransformerBlock -> proj_out -> + residual.
+        proj_in / proj_out are 1x1 convolutions (SD1.5) or nn.Linear (SDXL, use_linear_projection):
+        on NHWC tokens both are the same GEMM."""
         B, H, W, C = x.shape
         S, M = H * W, B * H * W
+        level = self._level_of(p)
+        heads = self.cfg.heads(level)
         xf = x.view(M, C)
-        t = p + ".transformer_blocks.0"
         g = self.gn(p + ".norm", [xf], B, S, 1e-6, False, save)
         h = self.linear(p + ".proj_in", [g], lora, save=save)
-        n = self.ln(t + ".norm1", h, save)
-        q, k, v = self.linear_group(t + ".attn1.to_q", n, lora, save=save)
-        a = self.attention(q, k, v, B, S, S, save)
-        h = self.linear(t + ".attn1.to_out.0", [a], lora, residual=h, save=save)
-        n = self.ln(t + ".norm2", h, save)
-        q = self.linear(t + ".attn2.to_q", [n], lora, save=save)
-        k, v = self.linear_group(t + ".attn2.to_k", ctx, lora, save=save)
-        a = self.attention(q, k, v, B, S, ctx.shape[0] // B, save)
-        h = self.linear(t + ".attn2.to_out.0", [a], lora, residual=h, save=save)
-        n = self.ln(t + ".norm3", h, save)
-        u = self.linear(t + ".ff.net.0.proj", [n], lora, save=save)
-        gg = self._new(M, u.shape[1] // 2)
-        ops.geglu_fwd(u, gg)
-        if save is not None:
-            save.append(("geglu", u[:self._lrows(M)]))
-        h = self.linear(t + ".ff.net.2", [gg], lora, residual=h, save=save)
+        for d in range(self.cfg.depth(level)):
+            t = p + f".transformer_blocks.{d}"
+            n = self.ln(t + ".norm1", h, save)
+            q, k, v = self.linear_group(t + ".attn1.to_q", n, lora, save=save)
+            a = self.attention(q, k, v, B, S, S, save, heads)
+            h = self.linear(t + ".attn1.to_out.0", [a], lora, residual=h, save=save)
+            n = self.ln(t + ".norm2", h, save)
+            q = self.linear(t + ".attn2.to_q", [n], lora, save=save)
+            k, v = self.linear_group(t + ".attn2.to_k", ctx, lora, save=save)
+            a = self.attention(q, k, v, B, S, ctx.shape[0] // B, save, heads)
+            h = self.linear(t + ".attn2.to_out.0", [a], lora, residual=h, save=save)
+            n = self.ln(t + ".norm3", h, save)
+            u = self.linear(t + ".ff.net.0.proj", [n], lora, save=save)
+            gg = self._new(M, u.shape[1] // 2)
+            ops.geglu_fwd(u, gg)
+            if save is not None:
+                save.append(("geglu", u[:self._lrows(M)]))
+            h = self.linear(t + ".ff.net.2", [gg], lora, residual=h, save=save)
         return self.linear(p + ".proj_out", [h], lora, residual=xf, save=save).view(B, H, W, C)
 
     def _lrows(self, n):
@@ -529,8 +545,10 @@ class UNetB200:
         lb, bt = self._lb
         return n * lb // bt
 
-    def forward(self, sample, timesteps, ctx, lora=True, save=False, lora_batch=None):
+    def forward(self, sample, timesteps, ctx, lora=True, save=False, lora_batch=None, added_cond=None):
         """sample: fp32 [B,H,W,4] NHWC; timesteps: int64 [B]; ctx: bf16 [B*77, D].
+        added_cond (SDXL `added_cond_kwargs`, train_pcm_lora_sdxl_adv.py:1094-1133): (text_embeds bf16
+        [B, text_embed_dim], time_ids int64 [B, 6]).
         Returns eps fp32 [B,H,W,4] (values rounded to bf16 like the autocast output).
 
         lora_batch = b < B runs ONE pass in which only the first b samples carry the LoRA adapter
@@ -546,7 +564,20 @@ class UNetB200:
         emb = self._new(B, c0)
         ops.timestep_embed(timesteps, emb)
         hemb = self.linear("time_embedding.linear_1", [emb], False, act=1)
-        st = self.linear("time_embedding.linear_2", [hemb], False, act=1)  # silu(temb)
+        if not cfg.addition_embed:
+            st = self.linear("time_embedding.linear_2", [hemb], False, act=1)  # silu(temb)
+        else:
+            # "text_time": emb = time_embedding(t) + add_embedding(cat[text_embeds, sinusoid(time_ids)]);
+            # every consumer takes silu(emb): the sum and the SiLU run in the last GEMM's epilogue
+            if added_cond is None:
+                raise ValueError("this UNet needs added_cond = (text_embeds, time_ids) (addition_embed_type text_time)")
+            text_embeds, time_ids = added_cond
+            temb = self.linear("time_embedding.linear_2", [hemb], False)
+            tid = self._new(B * cfg.num_time_ids, cfg.addition_time_embed_dim)
+            ops.timestep_embed(time_ids.reshape(-1), tid)
+            add_in = torch.cat([text_embeds.to(BF16), tid.view(B, -1)], dim=1).contiguous()  # [B, 2816] glue
+            ah = self.linear("add_embedding.linear_1", [add_in], False, act=1)
+            st = self.linear("add_embedding.linear_2", [ah], False, residual=temb, act=1)
         self._temb = self.temb_all(st, lora) if self.temb_group is not None else None
         x = self._new(B, H, W, c0)
         Lci = self.layers["conv_in"]
@@ -770,8 +801,7 @@ class UNetB200:
         return dx
 
     def attn_bwd(self, rec, dout):
-        _, q, k, v, out, lse, B, Sq, Skv = rec
-        Hh = self.cfg.num_heads
+        _, q, k, v, out, lse, B, Sq, Skv, Hh = rec
         D = q.shape[1] // Hh
         Cc = q.shape[1]
         if q.stride(0) == 3 * Cc:     # self-attention: q/k/v are column views of one [M, 3C] matrix
@@ -811,28 +841,34 @@ class UNetB200:
         return self.gn_bwd(gn1, dh.view(M, -1), add=dsc)
 
     def transformer_bwd(self, recs, dout):
-        """recs order as appended by transformer(); dout [B,H,W,C]; returns dx [B,H,W,C]."""
-        (gn, pin, ln1, lqkv, at1, lo1, ln2, lq2, lkv2, at2, lo2, ln3, ff1, gegl, ff2, pout) = recs
+        """recs order as appended by transformer(): gn, proj_in, depth x 13 block records, proj_out;
+        dout [B,H,W,C]; returns dx [B,H,W,C]."""
+        gn, pin, pout = recs[0], recs[1], recs[-1]
+        blocks = recs[2:-1]
+        assert len(blocks) % 13 == 0
         B, H, W, C = dout.shape
         M = B * H * W
         do = dout.view(M, C)
-        dh3 = self.linear_bwd(pout, do)
-        dgg = self.linear_bwd(ff2, dh3)
-        u = gegl[1]
-        du = torch.empty_like(u)
-        ops.geglu_bwd(dgg, u, du)
-        dn3 = self.linear_bwd(ff1, du)
-        dh2 = self.ln_bwd(ln3, dn3, add=dh3)
-        da2 = self.linear_bwd(lo2, dh2)
-        dq2, dkv2 = self.attn_bwd(at2, da2)
-        self.linear_group_bwd(lkv2, dkv2, need_dx=False)
-        dn2 = self.linear_bwd(lq2, dq2)
-        dh1 = self.ln_bwd(ln2, dn2, add=dh2)
-        da1 = self.linear_bwd(lo1, dh1)
-        _, dqkv = self.attn_bwd(at1, da1)
-        dn1 = self.linear_group_bwd(lqkv, dqkv)
-        dh0 = self.ln_bwd(ln1, dn1, add=dh1)
-        dg = self.linear_bwd(pin, dh0)
+        dh = self.linear_bwd(pout, do)
+        for bi in reversed(range(len(blocks) // 13)):
+            (ln1, lqkv, at1, lo1, ln2, lq2, lkv2, at2, lo2, ln3, ff1, gegl, ff2) = blocks[13 * bi:13 * bi + 13]
+            dh3 = dh
+            dgg = self.linear_bwd(ff2, dh3)
+            u = gegl[1]
+            du = torch.empty_like(u)
+            ops.geglu_bwd(dgg, u, du)
+            dn3 = self.linear_bwd(ff1, du)
+            dh2 = self.ln_bwd(ln3, dn3, add=dh3)
+            da2 = self.linear_bwd(lo2, dh2)
+            dq2, dkv2 = self.attn_bwd(at2, da2)
+            self.linear_group_bwd(lkv2, dkv2, need_dx=False)
+            dn2 = self.linear_bwd(lq2, dq2)
+            dh1 = self.ln_bwd(ln2, dn2, add=dh2)
+            da1 = self.linear_bwd(lo1, dh1)
+            _, dqkv = self.attn_bwd(at1, da1)
+            dn1 = self.linear_group_bwd(lqkv, dqkv)
+            dh = self.ln_bwd(ln1, dn1, add=dh1)
+        dg = self.linear_bwd(pin, dh)
         dx, _ = self.gn_bwd(gn, dg, add=do)
         return dx.view(B, H, W, C)
 

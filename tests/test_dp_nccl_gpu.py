@@ -73,6 +73,8 @@ def _worker(rank, world, port, out, use_graph):
         out["update_size"] = (params["w"] - solo.unet.lora_master.cpu()).abs().max().item()
         out["num_lora"] = len(names)
     dist.barrier()
+    st.graph = st.graph_opt = None
+    torch.cuda.synchronize()
     dist.destroy_process_group()
 
 

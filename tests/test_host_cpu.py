@@ -37,13 +37,18 @@ def test_clip_and_adamw_ref_matches_torch_optim():
 def test_product_tables_equal_oracle_tables():
     from oracle import unet_ref
     from pcm_b200 import config, weights
-    for name in ("SD15", "TINY"):
+    for name in ("SD15", "TINY", "SDXL", "TINY_XL"):
         o, p = getattr(unet_ref, name), getattr(config, name)
         assert unet_ref.layer_table(o) == config.layer_table(p)
-    a = unet_ref.init_params(unet_ref.TINY, 3)
-    b = weights.synthetic_state_dict(config.TINY, 3)
-    assert a.keys() == b.keys()
-    assert all(torch.equal(a[k], b[k]) for k in a)
+    for name in ("TINY", "TINY_XL"):
+        a = unet_ref.init_params(getattr(unet_ref, name), 3)
+        b = weights.synthetic_state_dict(getattr(config, name), 3)
+        assert a.keys() == b.keys()
+        assert all(torch.equal(a[k], b[k]) for k in a)
+    # SDXL inventory: 2.567 B base parameters, transformer depth 1 / 2 / 10
+    tab = config.layer_table(config.SDXL)
+    assert sum(1 for t in tab if ".transformer_blocks.9.attn1.to_q" in t[0]) == 6   # depth-10 stacks: 2 down + mid + 3 up
+    assert any(t[0] == "add_embedding.linear_1" and t[2] == 2816 for t in tab)
 
 
 @pytest.mark.parametrize("name", ["constant", "constant_with_warmup", "linear", "cosine", "cosine_with_restarts",
