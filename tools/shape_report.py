@@ -19,9 +19,11 @@ print("dry-run kernels:", len(rec), "gemms:", len(gemms))
 rows = list(csv.reader(open(csv_path)))
 hi = next(i for i, r in enumerate(rows) if 'Kernel Name' in r)
 hdr = rows[hi]; ki = hdr.index('Kernel Name'); vi = hdr.index('Metric Value'); ui = hdr.index('Metric Unit')
+mi = hdr.index('Metric Name')
 dur = []
 for r in rows[hi + 1:]:
-    if len(r) > vi and 'pcm_gemm_kernel' in r[ki]:
+    if len(r) > vi and r[mi] == 'gpu__time_duration.sum' and \
+            ('pcm_gemm_kernel' in r[ki] or 'pcm_gemm_epi2_kernel' in r[ki] or 'pcm_gemm2_kernel' in r[ki]):
         v = float(r[vi].replace(',', '')); u = r[ui]
         v *= {'us': 1e-6, 'ns': 1e-9, 'ms': 1e-3}.get(u, 1.0)
         dur.append(v)
