@@ -172,6 +172,12 @@ int pcm_add_noise(const float* x, const float* noise, const double* coef, int64_
  * pred_type: 0 = epsilon, 1 = v_prediction (predicted_origin, T15:268-280) */
 int pcm_teacher_step(const float* eps_c, const float* eps_u, const float* noisy, const double* coef,
                      int64_t per, int B, int pred_type, float* x_prev, void* stream);
+/* Opt-in multi-substep teacher solve (num_substeps > 1; the reference does ONE step, T15:1217-1258):
+ * one DDIM sub-step t_cur[b] -> t_next[b] (t_next < 0 = the solver's alpha_cumprods[0] entry) of the
+ * CFG-mixed prediction; with a single sub-step it equals pcm_teacher_step bit for bit */
+int pcm_teacher_substep(const float* eps_c, const float* eps_u, const float* x_cur,
+                        const float* alphas_cumprod, const int64_t* t_cur, const int64_t* t_next,
+                        const double* coef, int64_t per, int B, int pred_type, float* x_next, void* stream);
 /* T15:1200-1212 + 1269-1293: loss (0 = huber, 1 = l2), d loss / d eps_student, optional dumps */
 int pcm_loss(const float* eps_s, const float* eps_t, const float* noisy, const float* x_prev,
              const double* coef, int64_t per, int B, int loss_type, float huber_c, int pred_type,

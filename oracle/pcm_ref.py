@@ -101,7 +101,7 @@ def noise_travel(alphas_cumprod, x, noise, t_cur, t_tgt):  # S15:526-554
 
 def pcm_step_ref(cfg, params, batch, *, multiphase, num_ddim=50, loss_type="huber", huber_c=1e-3,
                  prediction_type="epsilon", apply_cfg_solver=True, emulate_bf16=False,
-                 need_grad=True, round_eps_bf16=None):
+                 need_grad=True, round_eps_bf16=None, teacher_substeps=1):
     """One iteration of the reference loop, T15:1139-1293, on explicit inputs.
 
     batch: latents [B,4,H,W], noise, index [B] int64, w [B], prompt_embeds [B,77,D],
@@ -161,7 +161,27 @@ def pcm_step_ref(cfg, params, batch, *, multiphase, num_ddim=50, loss_type="hube
             eps_u, x0_u = eps_c, x0_c
         pred_x0 = x0_c + w4 * (x0_c - x0_u)                                   # T15:1254
         pred_noise = eps_c + w4 * (eps_c - eps_u)                             # T15:1255-1257
-        x_prev = solver.ddim_step(pred_x0, pred_noise, index)                 # T15:1258 (float64)
+        if teacher_substeps == 1:
+            x_prev = solver.ddim_step(pred_x0, pred_noise, index)             # T15:1258 (float64)
+        else:
+            # opt-in extension (not in the reference): k DDIM sub-steps over the same interval
+            k, dt = teacher_substeps, topk // teacher_substeps
+            acd = ac.double()
+            x_cur, t_cur = noisy, start_t
+            for j in range(k):
+                t_next = start_t - (j + 1) * dt
+                a_n = torch.where(t_next < 0, acd[0], acd[t_next.clamp(min=0)]).reshape(-1, 1, 1, 1)
+                x_next = a_n.sqrt() * pred_x0 + (1.0 - a_n).sqrt() * pred_noise
+                if j == k - 1:
+                    x_prev = x_next
+                    break
+                x_cur, t_cur = x_next.float(), t_next.clamp(min=0)
+                e_c = teacher(x_cur, t_cur, prompt, addc)
+                e_u = teacher(x_cur, t_cur, uncond, addu) if apply_cfg_solver else e_c
+                p_c = predicted_origin(e_c, t_cur, x_cur, prediction_type, alpha_schedule, sigma_schedule)
+                p_u = predicted_origin(e_u, t_cur, x_cur, prediction_type, alpha_schedule, sigma_schedule)
+                pred_x0 = p_c + w4 * (p_c - p_u)
+                pred_noise = e_c + w4 * (e_c - e_u)
 
         eps_t = student(x_prev.float(), t, prompt, addc)                      # T15:1263-1268
         x0_t = predicted_origin(eps_t, t, x_prev, prediction_type, alpha_schedule, sigma_schedule)

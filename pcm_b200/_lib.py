@@ -103,6 +103,7 @@ EXPORTS = [
     "pcm_prepare",
     "pcm_add_noise",
     "pcm_teacher_step",
+    "pcm_teacher_substep",
     "pcm_loss",
     "pcm_noise_travel",
     "pcm_axpby_f64",
@@ -137,6 +138,7 @@ ARGTYPES = {
     "pcm_prepare": [P, I, I, P, I, P, P, I, I, P, P, P, P, P],
     "pcm_add_noise": [P, P, P, L64, I, I, P, P],
     "pcm_teacher_step": [P, P, P, P, L64, I, I, P, P],
+    "pcm_teacher_substep": [P, P, P, P, P, P, P, L64, I, I, P, P],
     "pcm_loss": [P, P, P, P, P, L64, I, I, F, I, P, P, P, P, P],
     "pcm_noise_travel": [P, P, P, P, P, L64, I, P, P],
     "pcm_axpby_f64": [P, P, P, P, L64, I, P, P],

@@ -340,3 +340,51 @@ extern "C" int pcm_fm_step(const float* x, const float* v, const float* z, const
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------
+// Opt-in multi-substep teacher solve: one DDIM sub-step of the CFG-mixed teacher prediction from
+// train timestep t_cur[b] to t_next[b] (the reference takes the whole DDIM interval in ONE step,
+// T15:1217-1258; with num_substeps = 1 this kernel reproduces pcm_teacher_step bit for bit).
+// alpha / sigma at t_cur are the fp32 schedule values (alpha_schedule / sigma_schedule, T15:808-809);
+// the target point uses acp[t_next] in double like DDIMSolver.ddim_alpha_cumprods_prev
+// (t_next < 0 -> acp[0], the solver's convention for its first entry, T15:297-299).
+// ------------------------------------------------------------------------------------------
+namespace pcm {
+__global__ void pcm_teacher_substep_kernel(const float* __restrict__ eps_c, const float* __restrict__ eps_u,
+                                           const float* __restrict__ x_cur, const float* __restrict__ acp,
+                                           const long long* __restrict__ t_cur,
+                                           const long long* __restrict__ t_next,
+                                           const double* __restrict__ coef, long long per, long long total,
+                                           int pred_type, float* __restrict__ x_next) {
+  griddep_sync();
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long b = i / per;
+    const float a_cur = acp[t_cur[b]];
+    const float al = sqrtf(a_cur), sg = sqrtf(1.f - a_cur);
+    const long long tn = t_next[b];
+    const double an = static_cast<double>(tn < 0 ? acp[0] : acp[tn]);
+    const float w = static_cast<float>(coef[b * kCoefN + kW]);
+    const float ec = eps_c[i], eu = eps_u[i], xn = x_cur[i];
+    const float x0c = pred_type == 0 ? (xn - sg * ec) / al : al * xn - sg * ec;
+    const float x0u = pred_type == 0 ? (xn - sg * eu) / al : al * xn - sg * eu;
+    const float px0 = x0c + w * (x0c - x0u);
+    const float pe = ec + w * (ec - eu);
+    x_next[i] = static_cast<float>(sqrt(an) * static_cast<double>(px0) + sqrt(1.0 - an) * static_cast<double>(pe));
+  }
+}
+}  // namespace pcm
+
+extern "C" int pcm_teacher_substep(const float* eps_c, const float* eps_u, const float* x_cur,
+                                   const float* alphas_cumprod, const int64_t* t_cur,
+                                   const int64_t* t_next, const double* coef, int64_t per, int B,
+                                   int pred_type, float* x_next, void* stream) {
+  const long long total = per * B;
+  if (pred_type != 0 && pred_type != 1) return set_error("pcm_teacher_substep: bad prediction type");
+  CUDA_TRY(launch_pdl(pcm_teacher_substep_kernel, dim3(grid_for(total)), dim3(256), 0, ST(stream), eps_c, eps_u,
+                      x_cur, alphas_cumprod, reinterpret_cast<const long long*>(t_cur),
+                      reinterpret_cast<const long long*>(t_next), coef, static_cast<long long>(per), total,
+                      pred_type, x_next));
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}

@@ -35,11 +35,19 @@ class PCMTrainStep:
                  num_ddim_timesteps=50, num_train_timesteps=1000, loss_type="huber", huber_c=1e-3,
                  lr=5e-6, betas=(0.9, 0.999), adam_eps=1e-8, weight_decay=1e-2, max_grad_norm=1.0,
                  apply_cfg_solver=True, bf16_mode=True, alphas_cumprod=None, process_group=None,
-                 keep_debug=False, prediction_type="epsilon", ema_decay=None, grad_buckets=4):
+                 keep_debug=False, prediction_type="epsilon", ema_decay=None, grad_buckets=4,
+                 teacher_substeps=1):
         """prediction_type: "epsilon" | "v_prediction" (predicted_origin, T15:268-280).
         ema_decay: None (reference behaviour: the target network IS the student, update_ema is never
         called, T15:1261-1268) or a rate in (0, 1): opt-in EMA target, updated after every optimiser
-        step as update_ema does (T15:344-355)."""
+        step as update_ema does (T15:344-355).
+        teacher_substeps: 1 (reference behaviour: ONE DDIM step of the teacher over the 20-timestep
+        interval, T15:1217-1258) or k > 1 dividing the interval: the teacher is evaluated k times along
+        it (opt-in multi-substep solve; each extra sub-step costs two more teacher forwards)."""
+        ratio = num_train_timesteps // num_ddim_timesteps
+        if teacher_substeps < 1 or ratio % teacher_substeps != 0:
+            raise ValueError(f"teacher_substeps must divide the DDIM interval ({ratio} train timesteps)")
+        self.substeps, self.sub_dt = teacher_substeps, ratio // teacher_substeps
         if prediction_type not in ("epsilon", "v_prediction"):
             raise ValueError(f"Prediction type {prediction_type} currently not supported.")  # T15:277-278
         self.pred_type = 0 if prediction_type == "epsilon" else 1
@@ -146,7 +154,10 @@ class PCMTrainStep:
             else:
                 eps_c = u.forward(self.noisy, self.start_t, self.in_prompt, lora=False, added_cond=added(0, B))
                 eps_u = eps_c
-        self.teacher_step_kernel(eps_c, eps_u)
+        if self.substeps == 1:
+            self.teacher_step_kernel(eps_c, eps_u)
+        else:
+            self._teacher_substeps(eps_c, eps_u, added)
         if self.ema_master is not None:      # opt-in EMA target: same network, EMA LoRA factors
             u.refresh_lora(self.ema_master)
         eps_t = u.forward(self.x_prev, self.t, self.in_prompt, lora=True, added_cond=added(0, B))
@@ -162,6 +173,29 @@ class PCMTrainStep:
             self.reducer.finish()
         else:
             u.backward(self.d_eps)
+
+    def _teacher_substeps(self, eps_c, eps_u, added):
+        """k DDIM sub-steps from start_t down to start_t - ratio (= t): the first uses the merged pass's
+        teacher outputs, each further one runs the frozen teacher (cond + uncond, batch 2B) again."""
+        u, B, k = self.unet, self.B, self.substeps
+        x_cur = self.noisy
+        t_cur = self.start_t
+        nb = 2 if self.apply_cfg else 1
+        for j in range(k):
+            t_next = self.start_t - (j + 1) * self.sub_dt          # -1 for index 0: the solver's acp[0] entry
+            out = self.x_prev if j == k - 1 else torch.empty_like(self.x_prev)
+            ops._call("pcm_teacher_substep", eps_c.data_ptr(), eps_u.data_ptr(), x_cur.data_ptr(),
+                      self.acp.data_ptr(), t_cur.data_ptr(), t_next.data_ptr(), self.coef.data_ptr(),
+                      self.per, B, self.pred_type, out.data_ptr())
+            if j == k - 1:
+                break
+            x_cur, t_cur = out, torch.clamp(t_next, min=0)
+            x2 = torch.cat([x_cur] * nb, 0)
+            t2 = torch.cat([t_cur] * nb, 0)
+            eps_cu = u.forward(x2, t2, self.in_ctx3[B * 77:(1 + nb) * B * 77], lora=False,
+                               added_cond=added(B, (1 + nb) * B))
+            eps_c = eps_cu[:B]
+            eps_u = eps_cu[B:] if self.apply_cfg else eps_c
 
     def teacher_step_kernel(self, eps_c, eps_u):
         """x_prev <- DDIM step of the CFG-mixed teacher prediction (T15:1224-1258), one launch."""

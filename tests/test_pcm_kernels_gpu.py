@@ -155,3 +155,22 @@ def test_prepare_bf16_mode_matches_reference_casts(cuda):
     sa = (ac[st.cpu()] ** 0.5).float()
     so = ((1 - ac[st.cpu()]) ** 0.5).float()
     assert torch.equal(coef[:, 10].cpu().float(), sa) and torch.equal(coef[:, 11].cpu().float(), so)
+
+
+def test_teacher_substep_single_equals_teacher_step(cuda):
+    """pcm_teacher_substep with ONE sub-step over the whole interval == pcm_teacher_step, bit for bit
+    (the reference behaviour is the k = 1 case of the opt-in multi-substep solve)."""
+    from pcm_b200 import ops
+    from pcm_b200.step import sd15_alphas_cumprod
+    B = len(INDEX)
+    d = _inputs(B, 5)
+    coef, st, t, et = _tables(cuda, 4, INDEX, d["w"])
+    ec, eu, xn = (_nhwc(d[k]).to(cuda) for k in ("eps_c", "eps_u", "noisy"))
+    a, b = torch.empty_like(xn), torch.empty_like(xn)
+    ops._call("pcm_teacher_step", ec.data_ptr(), eu.data_ptr(), xn.data_ptr(), coef.data_ptr(), PER, B, 0, a.data_ptr())
+    acp = sd15_alphas_cumprod().to(cuda)
+    t_next = st - 20
+    ops._call("pcm_teacher_substep", ec.data_ptr(), eu.data_ptr(), xn.data_ptr(), acp.data_ptr(), st.data_ptr(),
+              t_next.data_ptr(), coef.data_ptr(), PER, B, 0, b.data_ptr())
+    torch.cuda.synchronize()
+    assert torch.equal(a, b)

@@ -165,3 +165,32 @@ def test_step_sd15_config1_loss(cuda):
     loss, rloss = st.loss.item(), ref["loss"].item()
     assert abs(loss - rloss) <= 5e-3 * abs(rloss), (loss, rloss)
     assert _relerr(_nchw(st.debug["eps_student"]).cpu(), ref["eps_student"]) < 3e-2
+
+
+def test_step_teacher_substeps_and_ema_options(cuda):
+    """Opt-in extensions the north-star names (not used by the reference loop): a 2-substep teacher
+    solve against the oracle's restatement, and the EMA target (update_ema, T15:344-355)."""
+    from oracle import pcm_ref
+    from pcm_b200.step import PCMTrainStep
+    ocfg, pcfg, P, batch = _setup("TINY", 2, 16, 3)
+    ref = pcm_ref.pcm_step_ref(ocfg, P, batch, multiphase=4, emulate_bf16=True, need_grad=False, teacher_substeps=2)
+    ref1 = pcm_ref.pcm_step_ref(ocfg, P, batch, multiphase=4, emulate_bf16=True, need_grad=False)
+    st = PCMTrainStep(pcfg, P, cuda, batch=2, height=16, width=16, multiphase=4, keep_debug=True,
+                      teacher_substeps=2, ema_decay=0.95, lr=1e-3)
+    st.load_inputs(_nhwc(batch["latents"]), _nhwc(batch["noise"]), batch["index"], batch["w"],
+                   batch["prompt_embeds"].to(BF), batch["uncond_prompt_embeds"].to(BF))
+    st.forward_backward()
+    torch.cuda.synchronize()
+    e2 = _relerr(_nchw(st.x_prev).cpu(), ref["x_prev"])
+    e1 = _relerr(_nchw(st.x_prev).cpu(), ref1["x_prev"])
+    assert e2 < 2e-2 and e2 < e1, (e2, e1)          # matches the 2-substep oracle, not the 1-step one
+    with pytest.raises(ValueError):
+        PCMTrainStep(pcfg, P, cuda, batch=2, height=16, width=16, teacher_substeps=3)
+    # EMA copy: equal to the student before the first update, rate * old + (1 - rate) * new after it
+    before = st.unet.lora_master.clone()
+    assert torch.equal(st.ema_master, before)
+    st.optimizer_step()
+    torch.cuda.synchronize()
+    expect = before * 0.95 + st.unet.lora_master * (1 - 0.95)
+    assert torch.allclose(st.ema_master, expect, rtol=1e-6, atol=1e-8)
+    assert not torch.equal(st.unet.lora_master, before)
