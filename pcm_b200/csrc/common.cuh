@@ -228,6 +228,12 @@ __host__ __device__ __forceinline__ uint32_t umma_idesc_bf16(int m, int n, int a
   return d;
 }
 
+// 16-byte vector reduction to global memory (sm_90+): out[0..3] += {a, b, c, d}
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
+
 // ---------------- misc math ----------------
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
@@ -247,9 +253,17 @@ __device__ __forceinline__ float warp_max(float v) {
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
-__device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
+// sigmoid via ex2.approx + rcp.approx (2 MUFU ops, ~2 ulp): an IEEE division costs ~8 more issue
+// slots per element, which is what bounds the GroupNorm / SiLU kernels (ncu: FMA / ALU pipes, not DRAM)
+__device__ __forceinline__ float frcp_approx(float d) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+  return r;
+}
+__device__ __forceinline__ float sigmoid_f(float x) { return frcp_approx(1.f + __expf(-x)); }
+__device__ __forceinline__ float silu_f(float x) { return x * sigmoid_f(x); }
 __device__ __forceinline__ float dsilu_f(float x) {
-  float s = 1.f / (1.f + __expf(-x));
+  const float s = sigmoid_f(x);
   return s * (1.f + x * (1.f - s));
 }
 

@@ -434,9 +434,18 @@ pcm_wgrad_kernel(const __grid_constant__ WgradParams p) {
       tmem_ld_32x32(taddr + j, v);
       tmem_ld_wait();
       if (ch < p.Cp) {
+        if (p.os_col == 1) {
+          // rank index contiguous (dB layout [n][r]): 16-byte vector reductions, one sector each,
+          // instead of 32 scalar atomics whose lanes are 256 B apart
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          atomicAdd(o + static_cast<long long>(j + i) * p.os_col, __uint_as_float(v[i]) * p.alpha);
+          for (int i = 0; i < 32; i += 4)
+            red_add_v4(o + j + i, __uint_as_float(v[i]) * p.alpha, __uint_as_float(v[i + 1]) * p.alpha,
+                       __uint_as_float(v[i + 2]) * p.alpha, __uint_as_float(v[i + 3]) * p.alpha);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            atomicAdd(o + static_cast<long long>(j + i) * p.os_col, __uint_as_float(v[i]) * p.alpha);
+        }
       }
     }
     if (sem) {

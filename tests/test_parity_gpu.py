@@ -26,9 +26,12 @@ pytestmark = pytest.mark.gpu
 BF = torch.bfloat16
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
-# measured on B200; asserted at <= 2x the measured error
-LOSS_TOL_BF16 = {1: 6e-3, 2: 2e-3}
-LOSS_TOL_FP32 = {1: 8e-2, 2: 8e-2}
+# measured on B200; asserted at <= ~2x the measured error.
+# Config 2 (N = 131072 loss terms): 2.7e-4 and 7.8e-5 on two builds -> 2e-3 (north-star 1e-3 met).
+# Config 1 (N = 4096 loss terms only): the loss is a mean of |model_pred - target| over few, noisy terms;
+# two builds with IDENTICAL tensor accuracy (rel-L2 eps 8.29e-3 both) measured 3.0e-3 and 6.8e-3 -> 1.5e-2.
+LOSS_TOL_BF16 = {1: 1.5e-2, 2: 2e-3}
+LOSS_TOL_FP32 = {1: 2e-2, 2: 1.2e-2}
 TENSOR_TOL_BF16 = 3e-2       # rel. L2 of eps / x_prev / model_pred / target vs the bf16 oracle
 TENSOR_TOL_FP32 = 6e-2
 
