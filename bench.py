@@ -96,6 +96,11 @@ def synth_batch(cfg, B, hw, seed, pinned=True):
         index=torch.randint(0, 50, (B,), generator=g(4)),
         w=4.0 + torch.rand(B, generator=g(5)),
     )
+    if cfg.addition_embed:   # SDXL: zero unconditional embeddings, pooled text embedding, time ids
+        t["uncond"] = torch.zeros_like(t["uncond"])
+        t["index"] = torch.randint(0, 40, (B,), generator=g(4))
+        t["text_embeds"] = torch.randn(B, cfg.text_embed_dim, generator=g(6)).bfloat16()
+        t["time_ids"] = torch.tensor([[hw * 8, hw * 8, 0, 0, hw * 8, hw * 8]] * B)
     if pinned and torch.cuda.is_available():
         t = {k: v.pin_memory() for k, v in t.items()}
     return t
@@ -228,6 +233,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--latent", type=int, default=64)
+    ap.add_argument("--model", default="sd15", choices=["sd15", "sdxl"],
+                    help="sdxl: BASELINE config 4 without the adversarial term (use --batch 4 --latent 128); "
+                         "not the headline metric")
     ap.add_argument("--multiphase", type=int, default=4)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -251,17 +259,19 @@ def main():
         os.environ.setdefault("NCCL_P2P_LEVEL", "NVL")
         dist.init_process_group("nccl", device_id=dev)
         pg = dist.group.WORLD
-    cfg = config.SD15
+    cfg = config.SD15 if args.model == "sd15" else config.SDXL
     B, hw = args.batch, args.latent
     sd = weights.synthetic_state_dict(cfg, seed=0)   # identical on every rank (DDP broadcast semantics)
     step = PCMTrainStep(cfg, sd, dev, batch=B, height=hw, width=hw, multiphase=args.multiphase,
+                        num_ddim_timesteps=50 if args.model == "sd15" else 40,
                         lr=5e-6, weight_decay=1e-3, max_grad_norm=1.0, process_group=pg)
     del sd
     host = [synth_batch(cfg, B, hw, seed=100 * (rank + 1) + i) for i in range(4)]  # per-rank seeds (T15:797)
 
     def load(i):
         h = host[i % len(host)]
-        step.load_inputs(h["latents"], h["noise"], h["index"], h["w"], h["prompt"], h["uncond"])
+        step.load_inputs(h["latents"], h["noise"], h["index"], h["w"], h["prompt"], h["uncond"],
+                         text_embeds=h.get("text_embeds"), time_ids=h.get("time_ids"))
 
     load(0)
     torch.cuda.synchronize()
@@ -375,6 +385,8 @@ def main():
                 "launches": len(recs), "gemm_ms_per_step": tot_ms, "gemm_flop_per_step": tot_fl,
                 "whole_step_achieved": FLOP_PER_SAMPLE_64 * B * (hw / 64.0) ** 2 / (ms_per_step * 1e-3) / 1e12,
                 "whole_step_frac": FLOP_PER_SAMPLE_64 * B * (hw / 64.0) ** 2 / (ms_per_step * 1e-3) / 1e12 / sus}
+        if args.model != "sd15":   # the 5F + A + 4L count of SURVEY 8(d) and the ncu traffic are the SD1.5 network's
+            roof["whole_step_achieved"] = roof["whole_step_frac"] = roof["traffic"] = None
     if world > 1:
         dist.barrier()
 
@@ -384,10 +396,12 @@ def main():
             times, cores, _ = cpu_reference_steps(3, 1)     # ~30 s of CPU work
             cpu = cpu_line(times, cores)
         line = {
-            "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
+            "metric": METRIC if args.model == "sd15" else f"distillation steps/sec (SDXL PCM-LoRA, bs={B}/GPU)",
+            "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"SD1.5 PCM-LoRA {args.multiphase}-phase, bs={B}/GPU, {hw * 8}x{hw * 8} "
+            "config": {"workload": f"{'SD1.5' if args.model == 'sd15' else 'SDXL (no adversarial term)'} PCM-LoRA "
+                                   f"{args.multiphase}-phase, bs={B}/GPU, {hw * 8}x{hw * 8} "
                                    f"({hw}x{hw}x4 latents), LoRA r=64, CFG solver on, Huber, AdamW",
                        "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
                        "cuda_graph": use_graph,

@@ -178,6 +178,7 @@ TAPS3 = [(kw - 1, kh - 1) for kh in range(3) for kw in range(3)]  # (dw, dh), ta
 # a wgrad tile then accumulate in split order
 WGRAD_SEM = None
 _DET = os.environ.get("PCM_DETERMINISTIC", "0") == "1"
+_SKIP_WGRAD = os.environ.get("PCM_DEBUG_SKIP_WGRAD", "0") == "1"
 
 
 def deterministic(on, device=None):
@@ -213,6 +214,8 @@ def wgrad(p_src, q_src, out, *, lin, M, geo=(1, 1), taps=((0, 0),), tap_off=(0,)
     LAUNCHES["count"] += 1
     if DRY_RUN is not None:
         DRY_RUN.append(("wgrad", dict(M=M, Cp=p_src.C, taps=len(taps))))
+        return out
+    if _SKIP_WGRAD:     # measurement aid only (PCM_DEBUG_SKIP_WGRAD=1): how much of the step the wgrads cost
         return out
     L.check(L.lib().pcm_wgrad(C.byref(d), _stream()), "pcm_wgrad")
     return out
