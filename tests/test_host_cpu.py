@@ -108,3 +108,28 @@ def test_checkpoint_rotation_and_resume_discovery(tmp_path):
     assert T.find_resume_path(out, "latest") == "checkpoint-30"
     assert T.find_resume_path(out, "/some/where/checkpoint-20") == "checkpoint-20"
     assert T.find_resume_path(str(tmp_path / "empty"), "latest") is None
+
+
+def test_parameter_counts_match_published_checkpoints():
+    """External anchor for the (otherwise unpinned) UNet restatement: the layer inventory reproduces the
+    parameter counts of the published checkpoints exactly - runwayml/stable-diffusion-v1-5 UNet
+    859,520,964 and stabilityai/stable-diffusion-xl-base-1.0 UNet 2,567,463,684 - and the peft wrapping
+    rule gives 278 LoRA modules / 67,252,224 LoRA parameters at r = 64 for SD1.5."""
+    from pcm_b200 import config
+
+    def count(cfg):
+        n = lora = mods = 0
+        for name, kind, cin, cout, k in config.layer_table(cfg):
+            if kind in ("gn", "ln"):
+                n += 2 * cout
+                continue
+            taps = k * k if kind == "conv" else 1
+            n += cout * cin * taps + (0 if kind == "linear_nobias" else cout)
+            if config.is_lora_target(name):
+                lora += cfg.lora_rank * (cin * taps + cout)
+                mods += 1
+        return n, lora, mods
+    n15, l15, m15 = count(config.SD15)
+    assert n15 == 859_520_964 and l15 == 67_252_224 and m15 == 278
+    nxl, lxl, mxl = count(config.SDXL)
+    assert nxl == 2_567_463_684 and mxl == 788
