@@ -29,11 +29,15 @@ typedef struct {
   int64_t sW, sH, sB; /* element strides of the W, H, B dims (C is contiguous) */
 } pcm_asrc;
 
-/* B-operand source: weights [N, K] row-major bf16 (K contiguous), leading dimension ld. */
+/* B-operand source: weights bf16.  kblocked = 0: [N, K] row-major (K contiguous), leading dimension ld.
+ * kblocked = 1: K-blocked [K/64][N][64] - the 64-wide K slice of ALL rows is contiguous, so the N x 64
+ * operand tile of a K block is one contiguous N*128-byte run in HBM (a row-major tile is N separate
+ * 128-byte segments K*2 bytes apart: ~1.2 TB/s measured when small-M layers stream their weights). */
 typedef struct {
   const void* ptr;
   int32_t K, N;
   int64_t ld;
+  int32_t kblocked;
 } pcm_bsrc;
 
 /* One K-program entry: nchunks consecutive 64-wide K blocks read from a[a_src] at channel a_c0..,

@@ -20,7 +20,7 @@ class ASrc(C.Structure):
 
 
 class BSrc(C.Structure):
-    _fields_ = [("ptr", C.c_void_p), ("K", C.c_int32), ("N", C.c_int32), ("ld", C.c_int64)]
+    _fields_ = [("ptr", C.c_void_p), ("K", C.c_int32), ("N", C.c_int32), ("ld", C.c_int64), ("kblocked", C.c_int32)]
 
 
 class KEntry(C.Structure):

@@ -250,6 +250,8 @@ int launch_gemm2(GemmParams& p, const pcm_gemm_desc* d, cudaStream_t stream) {
   // both are bound by the TMA pipeline depth that fits in shared memory.
   static const bool enabled = getenv("PCM_2CTA") != nullptr;
   if (!enabled || p.ksplit > 1) return 1;
+  for (int i = 0; i < d->num_b; ++i)
+    if (d->b[i].kblocked) return 1;   // the pair kernel keeps 2-D row-major weight maps
   const int bn = p.block_n;
   if (bn < 64 || (bn % 32) != 0) return 1;
   const int tiles_m1 = (p.M + 127) / 128;

@@ -31,9 +31,14 @@ static __device__ __noinline__ void gemm_epilogue_rows_generic(const GemmParams&
       const float4 a1 = *reinterpret_cast<const float4*>(srow + ((2 * cg + 1) ^ (rr & 7)) * 4);
       const float f[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
       float* wp = ws + static_cast<long long>(m) * p.N + n;
+      if (n + 8 <= p.N && (p.N & 3) == 0) {   // two 16-byte stores (rows are 16-byte aligned)
+        *reinterpret_cast<float4*>(wp) = make_float4(f[0] * p.alpha, f[1] * p.alpha, f[2] * p.alpha, f[3] * p.alpha);
+        *reinterpret_cast<float4*>(wp + 4) = make_float4(f[4] * p.alpha, f[5] * p.alpha, f[6] * p.alpha, f[7] * p.alpha);
+      } else {
 #pragma unroll
-      for (int e = 0; e < 8; ++e)
-        if (n + e < p.N) wp[e] = f[e] * p.alpha;
+        for (int e = 0; e < 8; ++e)
+          if (n + e < p.N) wp[e] = f[e] * p.alpha;
+      }
       continue;
     }
     const int b = m / p.epiHW;

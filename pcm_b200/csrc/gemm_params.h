@@ -31,6 +31,7 @@ struct alignas(64) GemmParams {
   int out_fp32, round_bf16;
   float alpha;
   int act;
+  int b_blocked;     // bit i: b_maps[i] is a K-blocked [K/64][N][64] source (3-D map)
   int dep_a_map;     // >= 0: A map written by the previous launch (late PDL wait), -1: none
   int filtered;      // some K entries carry an N range (per-tile K-block count varies)
   int ksplit;        // > 1: work item = (tile, K split); split s stores its fp32 partial sums to

@@ -128,7 +128,10 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
             else
               tma_load_4d(sa, &p.a_maps[en.a_map], &full_bar[stage], en.a_c0 + c * 64, en.dw,
                           h0 + en.dh, b0);
-            tma_load_2d(sb, &p.b_maps[en.b_map], &full_bar[stage], en.b_k0 + c * 64, n0);
+            if ((p.b_blocked >> en.b_map) & 1)   // K-blocked weights: (64, N, K/64) view, contiguous tile
+              tma_load_3d(sb, &p.b_maps[en.b_map], &full_bar[stage], 0, n0, (en.b_k0 >> 6) + c);
+            else
+              tma_load_2d(sb, &p.b_maps[en.b_map], &full_bar[stage], en.b_k0 + c * 64, n0);
             if (++stage == S) {
               stage = 0;
               phase ^= 1;
@@ -265,7 +268,8 @@ __global__ void splitk_finalize_kernel(const GemmParams p) {
     const float* wp = p.ws + static_cast<long long>(m) * p.N + n;
     if (vec) {
       float4 a0 = *reinterpret_cast<const float4*>(wp), a1 = *reinterpret_cast<const float4*>(wp + 4);
-      for (int k = 1; k < p.ksplit; ++k) {   // split order: reproducible
+#pragma unroll 4
+      for (int k = 1; k < p.ksplit; ++k) {   // split order: reproducible (loads of 4 slices in flight)
         const float4 b0 = *reinterpret_cast<const float4*>(wp + k * slice);
         const float4 b1 = *reinterpret_cast<const float4*>(wp + k * slice + 4);
         a0.x += b0.x; a0.y += b0.y; a0.z += b0.z; a0.w += b0.w;
@@ -555,16 +559,27 @@ static int launch_gemm(const pcm_gemm_desc* d, cudaStream_t stream) {
   }
   for (int i = 0; i < PCM_MAX_BSRC; ++i) {
     const pcm_bsrc& b = d->b[i < d->num_b ? i : 0];
-    cuuint64_t dims[2] = {static_cast<cuuint64_t>(b.K), static_cast<cuuint64_t>(b.N)};
-    cuuint64_t strides[1] = {static_cast<cuuint64_t>(b.ld) * 2};
-    cuuint32_t box[2] = {64, static_cast<cuuint32_t>(d->block_n)};
-    cuuint32_t estr[2] = {1, 1};
-    if (int rc = encode_tmap(&p.b_maps[i], b.ptr, 2, dims, strides, box, estr)) return rc;
+    if (b.kblocked) {   // [K/64][N][64]: 3-D view (k within block, n, K block)
+      if (b.K % 64 != 0) return set_error("pcm_gemm: K-blocked B source needs K % 64 == 0");
+      cuuint64_t dims[3] = {64, static_cast<cuuint64_t>(b.N), static_cast<cuuint64_t>(b.K / 64)};
+      cuuint64_t strides[2] = {128, static_cast<cuuint64_t>(b.N) * 128};
+      cuuint32_t box[3] = {64, static_cast<cuuint32_t>(d->block_n), 1};
+      cuuint32_t estr[3] = {1, 1, 1};
+      if (int rc = encode_tmap(&p.b_maps[i], b.ptr, 3, dims, strides, box, estr)) return rc;
+      if (i < d->num_b) p.b_blocked |= 1 << i;
+    } else {
+      cuuint64_t dims[2] = {static_cast<cuuint64_t>(b.K), static_cast<cuuint64_t>(b.N)};
+      cuuint64_t strides[1] = {static_cast<cuuint64_t>(b.ld) * 2};
+      cuuint32_t box[2] = {64, static_cast<cuuint32_t>(d->block_n)};
+      cuuint32_t estr[2] = {1, 1};
+      if (int rc = encode_tmap(&p.b_maps[i], b.ptr, 2, dims, strides, box, estr)) return rc;
+    }
   }
   int nkb = 0;
   for (int e = 0; e < d->num_prog; ++e) {
     const pcm_kentry& k = d->prog[e];
-    if (k.a_src < 0 || k.a_src >= d->num_a || k.b_src < 0 || k.b_src >= d->num_b || k.nchunks < 1)
+    if (k.a_src < 0 || k.a_src >= d->num_a || k.b_src < 0 || k.b_src >= d->num_b || k.nchunks < 1 ||
+        (k.b_k0 & 63) != 0)
       return set_error("pcm_gemm: bad K program entry");
     p.prog[e] = KEntry{k.a_src, k.b_src, k.dw, k.dh, k.nchunks, k.a_c0, k.b_k0, k.n_lo, k.n_hi, 0};
     {  // an A source with fewer rows than the output only feeds the leading M tiles (TMA would zero

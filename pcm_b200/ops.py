@@ -33,10 +33,21 @@ def asrc_mat(t):
     return L.ASrc(t.data_ptr(), Cc, M, 1, 1, t.stride(0), t.stride(0) * M, t.stride(0) * M)
 
 
+def kblock(w):
+    """[N, K] row-major -> K-blocked [K/64, N, 64] (see pcm_bsrc.kblocked): the frozen weights are
+    stored this way so that the N x 64 operand tile of a K block is contiguous in HBM."""
+    N, K = w.shape
+    assert K % 64 == 0
+    return w.reshape(N, K // 64, 64).permute(1, 0, 2).contiguous()
+
+
 def bsrc(w):
-    """B-operand source from bf16 weights [N, K] (K contiguous)."""
+    """B-operand source from bf16 weights: [N, K] row-major (K contiguous) or K-blocked [K/64, N, 64]."""
+    if w.dim() == 3:
+        assert w.dtype == BF16 and w.is_contiguous() and w.shape[2] == 64, (w.dtype, w.shape, w.stride())
+        return L.BSrc(w.data_ptr(), w.shape[0] * 64, w.shape[1], 64, 1)
     assert w.dtype == BF16 and w.dim() == 2 and w.stride(1) == 1, (w.dtype, w.shape, w.stride())
-    return L.BSrc(w.data_ptr(), w.shape[1], w.shape[0], w.stride(0))
+    return L.BSrc(w.data_ptr(), w.shape[1], w.shape[0], w.stride(0), 0)
 
 
 _NUM_SMS = None

@@ -139,6 +139,7 @@ class UNetB200:
             self.refresh_lora()
         self._build_groups(need_backward)
         self._build_temb_group()
+        self._block_weights()
         self.saved = None
         self._temb = None
         self._lb = (1, 1)
@@ -246,6 +247,29 @@ class UNetB200:
         out = self._new(B, G.n_total)
         ops.gemm(srcs, bs, prog, lin=True, M=B, N=G.n_total, out=out, bias=G.bias, block_n=G.bn)
         return out, T
+
+    def _block_weights(self):
+        """Store every frozen GEMM weight K-blocked ([K/64][N][64], pcm_bsrc.kblocked): the operand tile of
+        a K block becomes one contiguous run in HBM.  Matters for the small-M layers (8x8 / 16x16 levels,
+        target pass), which stream their weights once per launch: 1.2 TB/s with row-major tiles (N separate
+        128-byte segments K*2 bytes apart).  PCM_KBLOCK=0 keeps the row-major layout."""
+        import os as _os
+        if _os.environ.get("PCM_KBLOCK", "1") == "0":
+            return
+        members = set()
+        for G in list(self.groups.values()) + ([self.temb_group] if self.temb_group is not None else []):
+            members.update(id(L) for L in G.layers)
+            G.w_stack = ops.kblock(G.w_stack)
+            if getattr(G, "w_t_cat", None) is not None:
+                G.w_t_cat = ops.kblock(G.w_t_cat)
+        for L in self.layers.values():
+            if id(L) in members:
+                L.w_fwd = None          # only reachable through the group's stacked operand
+                continue
+            if L.w_fwd is not None and L.w_fwd.dim() == 2:
+                L.w_fwd = ops.kblock(L.w_fwd)
+            if L.w_t is not None and L.w_t.dim() == 2:
+                L.w_t = ops.kblock(L.w_t)
 
     class _Side:
         """Run the enclosed launches on the wgrad side stream, ordered after everything enqueued so far

@@ -87,3 +87,19 @@ def test_model_call_shape(cuda):
     with pytest.raises(RuntimeError):
         student(x.cpu(), ts, encoder_hidden_states=ctx)
     assert student.parameters()[0] is net.lora_master and teacher.parameters() == []
+
+
+def test_sdxl_entry_point(cuda, tmp_path):
+    """train_pcm_lora_sdxl_adv: same flags as the reference script, consistency step only."""
+    from pcm_b200 import config, train_pcm_lora_sdxl_adv as TX
+    with pytest.raises(ValueError, match="adversarial"):
+        TX.parse_args(["--synthetic"])                                   # default --adv_weight 0.1
+    a = TX.parse_args(["--synthetic", "--adv_weight", "0", "--output_dir", str(tmp_path), "--train_batch_size", "2",
+                       "--resolution", "128", "--multiphase", "4", "--num_ddim_timesteps", "40", "--loss_type", "huber",
+                       "--seed", "1", "--mixed_precision", "bf16", "--max_train_steps", "2", "--log_every", "1",
+                       "--checkpointing_steps", "100", "--w_min", "4", "--w_max", "5", "--adv_lr", "1e-5"])
+    assert a._base_cfg is config.SDXL
+    a._cfg = config.TINY_XL                                              # narrow network for the test
+    st = TX.main(a)
+    assert st.opt_state[1].item() == 2.0 and torch.isfinite(st.loss).all()
+    assert (tmp_path / "adapter_model.safetensors").exists()

@@ -194,3 +194,43 @@ def test_grouped_linear_n_ranges(cuda, M, Ml, K, C, g):
     for i in range(g):
         ref3 += dT[:, i * 64:(i + 1) * 64].float() @ ats[i].float().t()
     _close(dx, ref3)
+
+
+@pytest.mark.parametrize("kind,shape", [("lin", (616, 768, 320)), ("conv", (2, 16, 16, 192, 96)), ("conv", (8, 8, 8, 1280, 256))])
+def test_kblocked_weights_bit_identical(cuda, kind, shape):
+    """K-blocked weight storage ([K/64][N][64], pcm_bsrc.kblocked) is a pure re-layout: same tiles, same
+    MMA order -> bit-identical output to the row-major source, also mixed with a row-major second source
+    (the LoRA s*B operand) in one K program, and through split-K."""
+    from pcm_b200 import ops
+    if kind == "lin":
+        M, K, N = shape
+        x = _rand((M, K), cuda, 1)
+        w = _rand((N, K), cuda, 2, K ** -0.5)
+        t = _rand((M, 64), cuda, 3)
+        sb = _rand((N, 64), cuda, 4, 0.1)
+        srcs = [ops.asrc_mat(x), ops.asrc_mat(t)]
+        prog = [(0, 0, 0, 0, K // 64, 0, 0), (1, 1, 0, 0, 1, 0, 0)]
+        kw = dict(lin=True, M=M, N=N)
+        ref = F.linear(x.float(), w.float()) + F.linear(t.float(), sb.float())
+    else:
+        B, H, W, Cin, N = shape
+        M = B * H * W
+        x = _rand((B, H, W, Cin), cuda, 1)
+        w4 = _rand((N, Cin, 3, 3), cuda, 2, (9 * Cin) ** -0.5)
+        w = _wmat_conv(w4)
+        t = _rand((B, H, W, 64), cuda, 3)
+        sb = _rand((N, 64), cuda, 4, 0.1)
+        srcs = [ops.asrc_nhwc(x), ops.asrc_nhwc(t)]
+        prog = [(0, 0, dw, dh, Cin // 64, 0, tt * Cin) for tt, (dw, dh) in enumerate(ops.TAPS3)] + [(1, 1, 0, 0, 1, 0, 0)]
+        kw = dict(lin=False, M=M, N=N, geo=(W, H))
+        ref = F.conv2d(x.float().permute(0, 3, 1, 2), w4.float(), None, padding=1).permute(0, 2, 3, 1).reshape(M, N)
+        ref = ref + F.linear(t.float().reshape(M, 64), sb.float())
+    wb = ops.kblock(w)
+    assert wb.shape == (w.shape[1] // 64, w.shape[0], 64)
+    o1 = torch.empty(M, N, device=cuda, dtype=torch.bfloat16)
+    o2 = torch.empty_like(o1)
+    ops.gemm(srcs, [ops.bsrc(w), ops.bsrc(sb)], prog, out=o1, **kw)
+    ops.gemm(srcs, [ops.bsrc(wb), ops.bsrc(sb)], prog, out=o2, **kw)
+    torch.cuda.synchronize()
+    _close(o1, ref)
+    assert torch.equal(o1, o2)

@@ -61,10 +61,10 @@ def test_grouped_layers_replace_single_launches(dry_step):
     assert net.groups
     for lead, G in net.groups.items():
         assert G.g in (2, 3)
-        assert G.w_stack.shape == (G.g * G.cout, G.cin)
+        # stacked frozen weights, stored K-blocked [K/64][N][64] (pcm_bsrc.kblocked)
+        assert G.w_stack.shape == (G.cin // 64, G.g * G.cout, 64)
         for i, L in enumerate(G.layers):
-            # member weights are views into the stacked operand
-            assert L.w_fwd.data_ptr() == G.w_stack[i * G.cout:].data_ptr()
+            assert L.w_fwd is None       # members are only reachable through the stacked operand
         if G.lora:
             r = net.r
             assert G.a_stack.shape == (G.g * r, G.cin)
