@@ -20,8 +20,8 @@ prefix and ``.default`` infix).
 (straight-through in autograd); this mirrors the reference running under bf16 autocast.
 """
 import math
-from dataclasses import dataclass, field
-from typing import Dict, Optional, Tuple
+from dataclasses import dataclass
+from typing import Dict, Tuple
 
 import torch
 import torch.nn.functional as F

@@ -14,7 +14,6 @@ therefore needs the sum of squares of the SUMMED gradient.
 import math
 import os
 
-import torch
 import torch.distributed as dist
 
 

@@ -18,7 +18,7 @@ import numpy as np
 import torch
 
 from . import ops
-from .solver import _axpby64, _require_cuda, extract_into_tensor
+from .solver import _axpby64, _require_cuda
 
 
 class EulerSolver:
