@@ -146,3 +146,14 @@ class PCMNoiseScheduler:
                   current_timesteps.to(x.device).long().contiguous().data_ptr(),
                   target_timesteps.to(x.device).long().contiguous().data_ptr(), x.numel() // B, B, out.data_ptr())
         return out.to(current_samples.dtype)
+
+
+def sample_adv_timesteps(end_timesteps, num_train_timesteps, multiphase, generator=None):
+    """Per-sample adversarial timesteps of the adversarial PCM variant
+    (train_pcm_lora_sd15_adv.py:1288-1298): adv_t[i] ~ U{end_t[i], ..., end_t[i] + T // multiphase - 1}.
+    The reference draws them in a Python loop with one `.item()` host sync per sample; this is the same
+    distribution drawn on the device in one call (no sync), ready for `PCMNoiseScheduler.noise_travel`."""
+    span = num_train_timesteps // multiphase
+    off = torch.randint(0, span, end_timesteps.shape, device=end_timesteps.device, dtype=end_timesteps.dtype,
+                        generator=generator)
+    return end_timesteps + off

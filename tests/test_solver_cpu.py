@@ -55,3 +55,15 @@ def test_error_behaviour_matches_reference():
         solver.predicted_origin(x, t, x, "sample", a, s)
     with pytest.raises(RuntimeError, match="no CPU fallback"):   # product path never computes on the host
         solver.predicted_origin(x, t, x, "epsilon", a, s)
+
+
+def test_sample_adv_timesteps_range():
+    """Device-side replacement of the per-sample randint loop (train_pcm_lora_sd15_adv.py:1288-1298)."""
+    import torch
+    from pcm_b200.solver import sample_adv_timesteps
+    end = torch.tensor([0, 239, 499, 739] * 64)
+    g = torch.Generator().manual_seed(0)
+    adv = sample_adv_timesteps(end, 1000, 4, generator=g)
+    assert adv.dtype == end.dtype and adv.shape == end.shape
+    assert bool((adv >= end).all()) and bool((adv < end + 250).all())
+    assert adv.unique().numel() > 100            # really random within the phase
