@@ -12,8 +12,15 @@
 // Replaces the cuDNN / cuBLAS calls that diffusers' UNet2DConditionModel + peft LoRA issue for
 // train_pcm_lora_sd15.py:1192-1198, 1219-1223, 1238-1244, 1263-1268 (forwards) and :1296
 // (backward).  Warp roles: warp0 = TMA producer, warp1 = MMA issuer (+TMEM alloc),
-// warps 2-9 = two epilogue groups (TMEM -> registers -> smem transposition -> global).  K-program
-// entries may be restricted to an output-column range (grouped Linear layers sharing their input).
+// warps 2-9 = epilogue.  Two epilogues share the mainloop (gemm_body<EPI2>): v1 = two groups,
+// TMEM -> registers -> smem transposition -> 16-byte coalesced stores (long-K convolutions, fp32 /
+// activation outputs, split-K partial sums); v2 = thread per accumulator row, TMA stores and TMA
+// residual boxes (gemm_epilogue_v2.cuh; default for bf16 outputs with <= 24 K blocks).
+// K-program entries may be restricted to an output-column range (grouped Linear layers sharing
+// their input) or to the leading M tiles (an A source with fewer rows than the output: the LoRA
+// T of the student samples in the merged student + teacher pass).  Weights may be K-blocked
+// ([K/64][N][64], pcm_bsrc.kblocked).  dep_a_src1: late programmatic-dependent-launch wait on the
+// LoRA down-projection, M tiles visited last-to-first.  split-K: ordered workspace slices + finalize.
 #include "common.cuh"
 #include "host_common.h"
 #include "../../include/pcm_b200.h"
