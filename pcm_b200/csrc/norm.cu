@@ -651,10 +651,17 @@ static int gn_launch_cfg(int C, int HW, int B, int* threads, int* ppb, int* nblk
   int ny = 512 / nvec;      // ny * nvec <= 512 threads  =>  ny * C <= 4096 staged floats
   if (ny < 1) ny = 1;
   *threads = nvec * ny;
-  // Two waves of blocks at two resident blocks per SM (all four kernels are built for <= 64 registers):
+  // ONE wave of blocks at two resident blocks per SM (all four kernels are built for <= 64 registers;
+  // PCM_GN_WAVES overrides):
   // the total block count is at most 2 x 2 x SMs, so there is no third, nearly empty wave (ncu showed
   // the SMs idle for 36 % of the kernel with 600 blocks on 296 slots)
-  int target_blocks = (4 * num_sms()) / B;
+  static int waves = -1;
+  if (waves < 0) {
+    const char* e = getenv("PCM_GN_WAVES");
+    waves = e ? atoi(e) : 1;   // measured: 1 wave 61 us, 2 waves 66 us, 3 waves 74 us (B=24, C=320 fwd)
+    if (waves < 1) waves = 1;
+  }
+  int target_blocks = (2 * waves * num_sms()) / B;
   if (target_blocks < 1) target_blocks = 1;
   int p = (HW + target_blocks - 1) / target_blocks;
   if (p < ny * 4) p = ny * 4;
