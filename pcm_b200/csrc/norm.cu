@@ -499,12 +499,15 @@ __global__ void __launch_bounds__(256, 4) ln_fwd_kernel(const bf16* __restrict__
                               float eps, bf16* __restrict__ out, float* __restrict__ stats) {
   griddep_sync();
   constexpr int RPW = 32 / LPR;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const int lane = threadIdx.x & 31;
   const int sub = lane % LPR;
+  const int nvec = C >> 3;
+  // grid-stride over groups of RPW rows: a few fat blocks per SM instead of thousands of one-shot blocks
+  for (int warp = warp0; warp * RPW < M; warp += nwarps) {
   const int r = warp * RPW + lane / LPR;
   const bool rvalid = r < M;
-  const int nvec = C >> 3;
   const bf16* row = x + static_cast<long long>(rvalid ? r : 0) * C;
   float f[kLnMaxVec][8];
   float s = 0.f;
@@ -537,7 +540,7 @@ __global__ void __launch_bounds__(256, 4) ln_fwd_kernel(const bf16* __restrict__
     }
   }
   const float rstd = rsqrtf(group_sum<LPR>(ss) / C + eps);
-  if (!rvalid) return;
+  if (!rvalid) continue;
   if (sub == 0 && stats) {
     stats[r * 2] = mean;
     stats[r * 2 + 1] = rstd;
@@ -563,6 +566,7 @@ __global__ void __launch_bounds__(256, 4) ln_fwd_kernel(const bf16* __restrict__
       u.w = pack_bf16x2(o[6], o[7]);
       *reinterpret_cast<uint4*>(orow + v * 8) = u;
     }
+  }
   }
 }
 
@@ -787,7 +791,13 @@ extern "C" int pcm_layernorm_fwd(const void* x, int M, int C, const float* gamma
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   const int wpb = 8, lpr = ln_lpr(C);
   const int rows_per_block = wpb * (32 / lpr);
-  const int grid = (M + rows_per_block - 1) / rows_per_block;
+  int grid = (M + rows_per_block - 1) / rows_per_block;
+  static int persist = -1;   // PCM_LN_PERSIST=0: one block per 8 x RPW rows (round-1 behaviour)
+  if (persist < 0) {
+    const char* e = getenv("PCM_LN_PERSIST");
+    persist = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  if (persist && grid > 4 * num_sms()) grid = 4 * num_sms();   // 4 resident blocks per SM, grid-stride
   const bf16* xp = reinterpret_cast<const bf16*>(x);
   bf16* op = reinterpret_cast<bf16*>(out);
   if (lpr == 8) CUDA_TRY(launch_pdl(ln_fwd_kernel<8>, dim3(grid), dim3(wpb * 32), 0, stream, xp, M, C, gamma, beta, eps, op, stats));
