@@ -124,3 +124,49 @@ def test_late_wait_launches_follow_their_producer(dry_step):
         assert prev[1].get("dep") is None, "two consecutive late-wait GEMMs"
         assert prev[1]["N"] == g["a_C"][g["dep"]], (prev[1]["N"], g["a_C"], g["dep"])
     assert n_dep > 100
+
+
+def _dry(cfg_name, **kw):
+    from pcm_b200 import config, ops, weights
+    from pcm_b200.step import PCMTrainStep
+    old = ops.DRY_RUN
+    ops.DRY_RUN = []
+    try:
+        cfg = getattr(config, cfg_name)
+        st = PCMTrainStep(cfg, weights.synthetic_state_dict(cfg, 0), "cpu", batch=2, height=16, width=16,
+                          multiphase=4, **kw)
+        ops.DRY_RUN.clear()
+        st.run_eager()
+        return st, collections.Counter(r[0] for r in ops.DRY_RUN), list(ops.DRY_RUN)
+    finally:
+        ops.DRY_RUN = old
+
+
+def test_sdxl_shaped_plan():
+    """SDXL-shaped network: transformer depth (1, 2, 3) -> 2*2 + 3*(2+1+... ) stacks; every K program valid;
+    the text_time embedding adds its two Linear layers and one more sinusoid launch per pass."""
+    from pcm_b200 import _lib, config
+    st, c, rec = _dry("TINY_XL", num_ddim_timesteps=40)
+    base, _, _ = _dry("TINY")
+    cfg = config.TINY_XL
+    # transformer blocks per pass: down (2 attn x depth) + mid + up (3 attn x depth), levels with attention only
+    blocks = sum(2 * cfg.depth(i) for i in range(3) if cfg.down_attn[i]) + cfg.depth(2) + \
+        sum(3 * cfg.depth(2 - i) for i in range(3) if cfg.up_attn[i])
+    assert c["pcm_geglu_fwd"] == 2 * blocks               # merged student + teacher pass, target pass
+    assert c["pcm_geglu_bwd"] == blocks
+    assert c["pcm_timestep_embed"] == 4                   # (t, time_ids) x 2 passes
+    for g in (r[1] for r in rec if r[0] == "gemm"):
+        assert len(g["prog"]) <= _lib.MAX_PROG and g["num_b"] <= _lib.MAX_BSRC
+        for e in g["prog"]:
+            assert e[6] % 64 == 0                          # b_k0 on a K-block boundary (K-blocked weights)
+
+
+def test_teacher_substeps_plan():
+    """k teacher sub-steps: k - 1 extra frozen-teacher passes (batch 2B, no tape) and k substep launches."""
+    _, c1, _ = _dry("TINY")
+    _, c2, rec2 = _dry("TINY", teacher_substeps=2)
+    assert c1["pcm_teacher_step"] == 1 and "pcm_teacher_substep" not in c1
+    assert c2["pcm_teacher_substep"] == 2 and "pcm_teacher_step" not in c2
+    assert c2["pcm_attn_fwd"] == c1["pcm_attn_fwd"] * 3 // 2      # 2 passes -> 3 passes
+    assert c2["pcm_attn_bwd"] == c1["pcm_attn_bwd"]               # the backward is the student's only
+    assert c2["wgrad"] == c1["wgrad"]
