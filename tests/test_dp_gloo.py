@@ -58,3 +58,36 @@ def test_rank_seeds_differ():
     from pcm_b200 import dp
     assert dp.rank_seed(5, 0) != dp.rank_seed(5, 1)
     assert dp.folded_coef(4.0, 2, 0.0) == (0.5, 1.0)
+
+
+def _worker_reducer(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    from pcm_b200 import dp
+    dp.init_process_group("gloo")
+    n = 1000
+    grad = torch.randn(n, generator=torch.Generator().manual_seed(dp.rank_seed(77, rank)))
+    local = grad.clone()
+    red = dp.GradReducer(grad, [0, 100, 250, 400, 700, 900], num_buckets=4)
+    assert red.world == world and len(red.buckets) == 4
+    red.start()
+    # the backward pass reports completed offsets from the END of the buffer, block by block
+    for lo in (900, 700, 400, 250, 100, 0):
+        red.ready(lo)
+    red.finish()
+    gathered = [torch.zeros(n) for _ in range(world)]
+    dist.all_gather(gathered, local)
+    out[rank] = (grad.clone(), sum(gathered))
+    dist.destroy_process_group()
+
+
+def test_grad_reducer_buckets_sum_to_flat_allreduce():
+    """The product's bucketed, backward-ordered all-reduce (dp.GradReducer, used by PCMTrainStep in eager
+    mode) gives exactly the flat SUM on every rank."""
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_reducer, args=(world, _free_port(), out), nprocs=world, join=True)
+    for r in range(world):
+        got, ref = out[r]
+        assert torch.equal(got, ref)
+    assert torch.equal(out[0][0], out[1][0])
