@@ -100,6 +100,18 @@ def pick_tiling(M, N, nkb):
     return pick_block_n(M, N), 1
 
 
+def gemm_flops(a_srcs, prog, M, N, lin, geo):
+    """ALGORITHMIC flops of one launch: an N-ranged K entry only counts its own output columns and an A
+    source with fewer rows than the output (the LoRA T of the leading samples) only its own rows."""
+    fl = 0.0
+    for e in prog:
+        a = a_srcs[e[0]]
+        rows = min(M, a.W if lin else a.B * geo[0] * geo[1])
+        cols = min(N, e[8] - e[7]) if (len(e) > 7 and e[8]) else N
+        fl += 2.0 * rows * cols * 64 * e[4]
+    return fl
+
+
 def gemm(a_srcs, b_srcs, prog, *, lin, M, N, out, geo=(1, 1), bias=None, rowvec=None,
          residual=None, out_strides=None, epi=None, alpha=1.0, act=0, round_bf16=False,
          block_n=None, ksplit=None, dep_a_src=None, splitk_ws=None):
@@ -168,7 +180,8 @@ def gemm(a_srcs, b_srcs, prog, *, lin, M, N, out, geo=(1, 1), bias=None, rowvec=
                                      nprog=len(prog), res=residual is not None, ksplit=d.ksplit,
                                      prog=[tuple(e) for e in prog], num_a=len(a_srcs), num_b=len(b_srcs),
                                      a_C=[a.C for a in a_srcs], b_K=[b.K for b in b_srcs],
-                                     b_N=[b.N for b in b_srcs], dep=dep_a_src)))
+                                     b_N=[b.N for b in b_srcs], dep=dep_a_src,
+                                     flop=gemm_flops(a_srcs, prog, M, N, lin, geo))))
         return out
     if PROFILE is not None:
         e0 = torch.cuda.Event(enable_timing=True, external=PROFILE_EXTERNAL)
@@ -176,7 +189,7 @@ def gemm(a_srcs, b_srcs, prog, *, lin, M, N, out, geo=(1, 1), bias=None, rowvec=
         e0.record()
         L.check(L.lib().pcm_gemm(C.byref(d), _stream()), "pcm_gemm")
         e1.record()
-        PROFILE.append((e0, e1, 2.0 * M * N * 64 * sum(e[4] for e in prog)))
+        PROFILE.append((e0, e1, gemm_flops(a_srcs, prog, M, N, lin, geo)))
         return out
     L.check(L.lib().pcm_gemm(C.byref(d), _stream()), "pcm_gemm")
     return out

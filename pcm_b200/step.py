@@ -143,10 +143,12 @@ class PCMTrainStep:
             eps_all = u.forward(self.noisy3[:nb * B], self.start_t3[:nb * B],
                                 self.in_ctx3 if nb == 3 else self.in_ctx3[:2 * B * 77],
                                 lora=True, save=True, lora_batch=B, added_cond=added(0, nb * B))
+            kv = u.last_ctx_kv
             eps_s, eps_c = eps_all[:B], eps_all[B:2 * B]
             eps_u = eps_all[2 * B:] if nb == 3 else eps_c
         else:
             eps_s = u.forward(self.noisy, self.start_t, self.in_prompt, lora=True, save=True, added_cond=added(0, B))
+            kv = u.last_ctx_kv
             if self.apply_cfg:
                 eps_cu = u.forward(self.noisy3[B:], self.start_t3[B:], self.in_ctx3[B * 77:], lora=False,
                                    added_cond=added(B, 3 * B))
@@ -154,13 +156,17 @@ class PCMTrainStep:
             else:
                 eps_c = u.forward(self.noisy, self.start_t, self.in_prompt, lora=False, added_cond=added(0, B))
                 eps_u = eps_c
+        # the target network is the student (same LoRA factors) on the same prompt embeddings
+        # (T15:1192-1198 vs 1263-1268): its cross-attention k / v ARE the student rows of the pass above
+        if kv is not None:
+            kv = u.ctx_kv_rows(kv, self.in_prompt.shape[0]) if self.ema_master is None else None
         if self.substeps == 1:
             self.teacher_step_kernel(eps_c, eps_u)
         else:
             self._teacher_substeps(eps_c, eps_u, added)
         if self.ema_master is not None:      # opt-in EMA target: same network, EMA LoRA factors
             u.refresh_lora(self.ema_master)
-        eps_t = u.forward(self.x_prev, self.t, self.in_prompt, lora=True, added_cond=added(0, B))
+        eps_t = u.forward(self.x_prev, self.t, self.in_prompt, lora=True, added_cond=added(0, B), ctx_kv=kv)
         if self.ema_master is not None:
             u.refresh_lora()
         self.loss_kernel(eps_s, eps_t)

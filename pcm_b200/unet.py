@@ -48,6 +48,15 @@ class UNetB200:
         self._temb_names = [n for n, *_ in tab if n.endswith(".time_emb_proj")]
         if not 2 <= len(self._temb_names) <= 23:
             self._temb_names = []
+        # every cross-attention k / v projection reads the same text context: a few grouped GEMMs per
+        # pass (chunks of <= 11 transformer blocks of one width, _build_ctx_group) instead of one per block
+        import os as _os0
+        self._ctx_names = [n for n, _, ci, *_ in tab if n.endswith((".attn2.to_k", ".attn2.to_v"))]
+        _co = {n: co for n, _, _, co, _ in tab}
+        self._ctx_names.sort(key=lambda n: _co[n])        # stable: blocks of one width become neighbours
+        if (_os0.environ.get("PCM_CTX_GROUP", "1") == "0" or len(self._ctx_names) < 4 or
+                len({ci for n, _, ci, *_ in tab if n in set(self._ctx_names)}) != 1):
+            self._ctx_names = []
         master, entries, opnd_total = [], [], 0
         moff = 0
         no_dgrad = ("attn2.to_k", "attn2.to_v", "time_emb_proj")
@@ -107,7 +116,7 @@ class UNetB200:
             for L, taps in entries:
                 if L.name in seen:
                     continue
-                grp = self._group_of(L.name)
+                grp = self._unit_of(L.name)
                 members = [by_name[n] for n in grp] if grp and all(n in by_name for n in grp) else [(L, taps)]
                 seen.update(m[0].name for m in members)
                 units.append(members)
@@ -139,9 +148,12 @@ class UNetB200:
             self.refresh_lora()
         self._build_groups(need_backward)
         self._build_temb_group()
+        self._build_ctx_group()
         self._block_weights()
         self.saved = None
         self._temb = None
+        self._ctxkv = self.last_ctx_kv = None
+        self._dkv_chunks = {}
         self._lb = (1, 1)
         # LoRA weight-gradient GEMMs are off the dgrad critical path (they only feed the optimiser):
         # they run on a side stream and fill SMs the main backward chain leaves idle
@@ -164,6 +176,13 @@ class UNetB200:
                 if name.endswith(suf):
                     return [name[:-len(suf)] + x for x in sufs]
         return None
+
+    def _unit_of(self, name):
+        """Layers whose LoRA operand copies are laid out kind-major next to each other: the shared-input
+        group of `name`, widened to ALL cross-attention k / v layers when they run as context chunks."""
+        if self._ctx_names and name.endswith((".attn2.to_k", ".attn2.to_v")):
+            return self._ctx_names
+        return self._group_of(name)
 
     def _build_groups(self, need_backward):
         """Stack the frozen weights (and view the kind-major LoRA operand copies) of every shared-input
@@ -248,6 +267,81 @@ class UNetB200:
         ops.gemm(srcs, bs, prog, lin=True, M=B, N=G.n_total, out=out, bias=G.bias, block_n=G.bn)
         return out, T
 
+    def _build_ctx_group(self):
+        """Cross-attention k / v of ALL transformer blocks from the text context (they depend on nothing
+        else): A copies of every layer stacked [n_layers*r, ctx_dim] for ONE down-projection GEMM, and the
+        frozen weights + s*B copies stacked per chunk (blocks of one width, at most 11 blocks = 22 N-ranged
+        LoRA entries + the base entry <= PCM_MAX_PROG)."""
+        self.ctx_group = None
+        if not self._ctx_names:
+            return
+        names = self._ctx_names
+        Ls = [self.layers[n] for n in names]
+        assert all(L.bias is None for L in Ls) and len(names) % 2 == 0
+        CG = types.SimpleNamespace(names=names, cin=Ls[0].cin, nl=len(names), chunks=[], where={})
+        CG.lora = all(L.lora is not None for L in Ls)
+        if CG.lora:
+            lo0, op = Ls[0].lora, self.lora_opnd
+            CG.a_stack = op[lo0.o_a_fwd:lo0.o_a_fwd + CG.nl * self.r * CG.cin].view(CG.nl * self.r, CG.cin)
+            assert Ls[-1].lora.a_fwd.data_ptr() == CG.a_stack[(CG.nl - 1) * self.r:].data_ptr()
+        cur = None
+        for b in range(len(names) // 2):
+            lead = names[2 * b]
+            assert lead.endswith(".attn2.to_k") and names[2 * b + 1] == lead[:-1] + "v"
+            G = self.groups[lead]
+            if cur is None or cur.cout != G.cout or len(cur.blocks) == 11:
+                cur = types.SimpleNamespace(cout=G.cout, blocks=[], first=2 * b)
+                CG.chunks.append(cur)
+            CG.where[lead[:-len(".attn2.to_k")]] = (len(CG.chunks) - 1, len(cur.blocks))
+            cur.blocks.append(G)
+        for ch in CG.chunks:
+            ch.n_total = 2 * ch.cout * len(ch.blocks)
+            assert ch.n_total < 65536
+            ch.bn = 160 if ch.cout % 160 == 0 else 64
+            ch.w_stack = torch.cat([G.w_stack for G in ch.blocks], 0).contiguous()
+            if CG.lora:
+                lo = self.layers[names[ch.first]].lora
+                ch.sb_stack = self.lora_opnd[lo.o_sb_fwd:lo.o_sb_fwd + ch.n_total * self.r].view(ch.n_total, self.r)
+                last = ch.blocks[-1].layers[-1].lora
+                assert last.sb_fwd.data_ptr() == ch.sb_stack[ch.n_total - ch.cout:].data_ptr()
+        self.ctx_group = CG
+
+    def ctx_kv_all(self, ctx, lora):
+        """{transformer block: (k, v, T)} for one pass: k / v are column views [M, C] of the chunk outputs,
+        T the block's two columns blocks [Ml, 2r] of the stacked LoRA down-projection (None without LoRA)."""
+        CG, r = self.ctx_group, self.r
+        M = ctx.shape[0]
+        Ml = self._lrows(M)
+        base = [(0, 0, 0, 0, CG.cin // 64, 0, 0)]
+        T = None
+        if lora and CG.lora:
+            T = self._new(Ml, CG.nl * r)
+            ops.gemm([ops.asrc_mat(ctx[:Ml])], [ops.bsrc(CG.a_stack)], base, lin=True, M=Ml, N=CG.nl * r, out=T)
+        outs = []
+        for ch in CG.chunks:
+            srcs, bs, prog = [ops.asrc_mat(ctx)], [ops.bsrc(ch.w_stack)], list(base)
+            if T is not None:
+                srcs.append(ops.asrc_mat(T))
+                bs.append(ops.bsrc(ch.sb_stack))
+                prog += [(1, 1, 0, 0, 1, (ch.first + i) * r, 0, i * ch.cout, (i + 1) * ch.cout)
+                         for i in range(2 * len(ch.blocks))]
+            out = self._new(M, ch.n_total)
+            ops.gemm(srcs, bs, prog, lin=True, M=M, N=ch.n_total, out=out, block_n=ch.bn)
+            outs.append(out)
+        kv = {}
+        for t, (c, j) in CG.where.items():
+            ch, out = CG.chunks[c], outs[c]
+            Cc = ch.cout
+            Tb = None if T is None else T[:, (ch.first + 2 * j) * r:(ch.first + 2 * j + 2) * r]
+            kv[t] = (out[:, 2 * j * Cc:(2 * j + 1) * Cc], out[:, (2 * j + 1) * Cc:(2 * j + 2) * Cc], Tb)
+        return kv
+
+    @staticmethod
+    def ctx_kv_rows(kv, rows):
+        """The leading `rows` context rows of a ctx_kv_all result (k / v only): the student samples'
+        projections of the merged pass, reused by the target pass (same context, same weights)."""
+        return {t: (k[:rows], v[:rows], None) for t, (k, v, _) in kv.items()}
+
     def _block_weights(self):
         """Store every frozen GEMM weight K-blocked ([K/64][N][64], pcm_bsrc.kblocked): the operand tile of
         a K block becomes one contiguous run in HBM.  Matters for the small-M layers (8x8 / 16x16 levels,
@@ -262,6 +356,9 @@ class UNetB200:
             G.w_stack = ops.kblock(G.w_stack)
             if getattr(G, "w_t_cat", None) is not None:
                 G.w_t_cat = ops.kblock(G.w_t_cat)
+        if self.ctx_group is not None:
+            for ch in self.ctx_group.chunks:
+                ch.w_stack = ops.kblock(ch.w_stack)
         for L in self.layers.values():
             if id(L) in members:
                 L.w_fwd = None          # only reachable through the group's stacked operand
@@ -552,7 +649,12 @@ class UNetB200:
             h = self.linear(t + ".attn1.to_out.0", [a], lora, residual=h, save=save)
             n = self.ln(t + ".norm2", h, save)
             q = self.linear(t + ".attn2.to_q", [n], lora, save=save)
-            k, v = self.linear_group(t + ".attn2.to_k", ctx, lora, save=save)
+            if self._ctxkv is not None:
+                k, v, Tkv = self._ctxkv[t]
+                if save is not None:
+                    save.append(("lgroup", t + ".attn2.to_k", ctx[:self._lrows(ctx.shape[0])], Tkv))
+            else:
+                k, v = self.linear_group(t + ".attn2.to_k", ctx, lora, save=save)
             a = self.attention(q, k, v, B, S, ctx.shape[0] // B, save, heads)
             h = self.linear(t + ".attn2.to_out.0", [a], lora, residual=h, save=save)
             n = self.ln(t + ".norm3", h, save)
@@ -569,7 +671,8 @@ class UNetB200:
         lb, bt = self._lb
         return n * lb // bt
 
-    def forward(self, sample, timesteps, ctx, lora=True, save=False, lora_batch=None, added_cond=None):
+    def forward(self, sample, timesteps, ctx, lora=True, save=False, lora_batch=None, added_cond=None,
+                ctx_kv=None):
         """sample: fp32 [B,H,W,4] NHWC; timesteps: int64 [B]; ctx: bf16 [B*77, D].
         added_cond (SDXL `added_cond_kwargs`, train_pcm_lora_sdxl_adv.py:1094-1133): (text_embeds bf16
         [B, text_embed_dim], time_ids int64 [B, 6]).
@@ -603,6 +706,14 @@ class UNetB200:
             ah = self.linear("add_embedding.linear_1", [add_in], False, act=1)
             st = self.linear("add_embedding.linear_2", [ah], False, residual=temb, act=1)
         self._temb = self.temb_all(st, lora) if self.temb_group is not None else None
+        # cross-attention k / v of every block: given (ctx_kv: another pass of this step already projected
+        # the same context with the same weights) or computed here in a few grouped GEMMs
+        if ctx_kv is not None:
+            assert not save
+            self._ctxkv = ctx_kv
+        else:
+            self._ctxkv = self.ctx_kv_all(ctx, lora) if self.ctx_group is not None else None
+        self.last_ctx_kv = self._ctxkv if lora else None
         x = self._new(B, H, W, c0)
         Lci = self.layers["conv_in"]
         ops.conv3x3_c4(sample, Lci.w_c4, Lci.bias, x, sgn=1, round_in=True)
@@ -831,9 +942,21 @@ class UNetB200:
         if q.stride(0) == 3 * Cc:     # self-attention: q/k/v are column views of one [M, 3C] matrix
             pk = self._new(q.shape[0], 3 * Cc)
             dq, dk, dv = pk[:, :Cc], pk[:, Cc:2 * Cc], pk[:, 2 * Cc:]
-        else:                         # cross-attention: k/v views of one [B*77, 2C] matrix
+        elif k.stride(0) == 2 * Cc:   # cross-attention: k/v views of one [B*77, 2C] matrix
             dq = self._new(q.shape[0], Cc)
             pk = self._new(k.shape[0], 2 * Cc)
+            dk, dv = pk[:, :Cc], pk[:, Cc:]
+        else:
+            # cross-attention, k/v are column windows of a context chunk [B*77, sum 2C] (ctx_kv_all):
+            # dk/dv go to the same window of a gradient matrix of that shape (the attention kernels
+            # address k and dk with one row stride); one matrix per chunk and backward pass
+            ld, col0 = k.stride(0), k.storage_offset() % k.stride(0)
+            assert v.stride(0) == ld and v.storage_offset() == k.storage_offset() + Cc
+            dq = self._new(q.shape[0], Cc)
+            key = (k.untyped_storage().data_ptr(), ld)
+            if key not in self._dkv_chunks:
+                self._dkv_chunks[key] = self._new(k.shape[0], ld)
+            pk = self._dkv_chunks[key][:, col0:col0 + 2 * Cc]
             dk, dv = pk[:, :Cc], pk[:, Cc:]
         delta = torch.empty_like(lse)
         ops.attn_bwd(q, k, v, out, dout, lse, delta, dq, dk, dv, B, Hh, Sq, Skv, D, D ** -0.5)
@@ -855,9 +978,12 @@ class UNetB200:
         # branch) are accumulated by the same kernel
         cs32 = self._new(B, cout, dtype=torch.float32)
         dh1, _ = self.gn_bwd(gn2, dh2.view(M, cout), colsum=cs32)
-        drow = self._new(B, cout)
-        ops.cast_f32_bf16(cs32, drow)
-        self.linear_bwd(tlin, drow, need_dx=False)
+        # the time-embedding branch ends in LoRA weight gradients only: all of it on the side stream
+        with UNetB200._Side(self, (cs32,)):
+            drow = self._new(B, cout)
+            ops.cast_f32_bf16(cs32, drow)
+            self._keep.append(drow)
+            self.linear_bwd(tlin, drow, need_dx=False)
         dh = self.conv3_bwd(conv1, dh1.view(B, H, W, cout), need_dx=need_dx)
         dsc = self.linear_bwd(recs[4], dout.view(M, cout), need_dx=need_dx) if has_sc else dout.view(M, cout)
         if not need_dx:
@@ -885,7 +1011,8 @@ class UNetB200:
             dh2 = self.ln_bwd(ln3, dn3, add=dh3)
             da2 = self.linear_bwd(lo2, dh2)
             dq2, dkv2 = self.attn_bwd(at2, da2)
-            self.linear_group_bwd(lkv2, dkv2, need_dx=False)
+            with UNetB200._Side(self, (dkv2,)):     # feeds weight gradients only: off the dgrad chain
+                self.linear_group_bwd(lkv2, dkv2, need_dx=False)
             dn2 = self.linear_bwd(lq2, dq2)
             dh1 = self.ln_bwd(ln2, dn2, add=dh2)
             da1 = self.linear_bwd(lo1, dh1)
@@ -902,6 +1029,7 @@ class UNetB200:
         grad_ready(offset): called (on the weight-gradient stream) after each block's backward with
         the flat-buffer offset from which every gradient element is final."""
         tape, marks, (B, H, W) = self.saved
+        self._dkv_chunks = {}
         boffs = self.block_grad_offsets() if grad_ready is not None else None
         pending = []
         cfg = self.cfg
