@@ -21,6 +21,8 @@ timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smok
 echo "smoke rc=$?" >> gpurun_out/smoke.log
 timeout 600 python bench.py --steps 20 > gpurun_out/bench.log 2>&1
 echo "bench rc=$?" >> gpurun_out/bench.log
+PCM_CTX_GROUP=0 timeout 200 python bench.py --steps 10 --no-cpu-baseline > gpurun_out/bench_noctx.log 2>&1
+echo "ctx-group off: $(tail -1 gpurun_out/bench_noctx.log | cut -c1-160)"
 timeout 120 python tools/gemm_bench.py > gpurun_out/gemm_bench.log 2>&1
 timeout 120 python tools/attn_bench.py > gpurun_out/attn_bench.log 2>&1
 timeout 120 python tools/norm_bench.py > gpurun_out/norm_bench.log 2>&1
