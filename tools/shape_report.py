@@ -33,7 +33,7 @@ assert len(dur) == len(gemms)
 agg = collections.defaultdict(lambda: [0, 0.0, 0.0])
 for g, t in zip(gemms, dur):
     key = (g['M'], g['N'], g['K'], g['bn'], g['lin'])
-    a = agg[key]; a[0] += 1; a[1] += t; a[2] += 2.0 * g['M'] * g['N'] * g['K']
+    a = agg[key]; a[0] += 1; a[1] += t; a[2] += g.get('flop', 2.0 * g['M'] * g['N'] * g['K'])   # algorithmic (ranged K entries)
 tot_t = sum(a[1] for a in agg.values()); tot_f = sum(a[2] for a in agg.values())
 print(f"total {tot_t*1e3:.2f} ms, {tot_f/1e12:.2f} TFLOP, {tot_f/tot_t/1e12:.1f} TFLOP/s")
 print("   ms    %time   n    M      N     K    bn lin  TF/s  tiles")
