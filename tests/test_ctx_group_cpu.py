@@ -6,67 +6,21 @@ with the per-layer definition  y = x W^T + s (x A^T) B^T  (peft LoRA Linear, SUR
 
 The interpreter reads the operands through the raw pointers of the descriptors, exactly what the CUDA side
 gets, so a wrong offset / stride / row range in the plan shows up here."""
-import ctypes
-
 import pytest
 import torch
 
-BF16 = torch.bfloat16
-
-
-def _mat(ptr, rows, cols, ld):
-    """bf16 [rows, cols] view (row stride ld elements) of raw memory."""
-    n = (rows - 1) * ld + cols
-    buf = (ctypes.c_uint16 * n).from_address(ptr)
-    flat = torch.frombuffer(buf, dtype=torch.int16).view(BF16)
-    return flat.as_strided((rows, cols), (ld, 1))
-
-
-def _interp_gemm(a_srcs, b_srcs, prog, *, lin, M, N, out, **kw):
-    """out[M, N] = sum over K entries of A_e[:, a_c0 : a_c0 + 64 n] @ B_e[n range, b_k0 : b_k0 + 64 n]^T,
-    fp32 accumulation, rows past an A source's extent read as zero (TMA zero fill)."""
-    assert lin and not kw.get("bias") and kw.get("residual") is None and not kw.get("act")
-    acc = torch.zeros(M, N, dtype=torch.float32)
-    for e in prog:
-        a, b = a_srcs[e[0]], b_srcs[e[1]]
-        kk = 64 * e[4]
-        rows = min(M, a.W)
-        A = _mat(a.ptr, rows, a.C, a.sW)[:, e[5]:e[5] + kk].float()
-        if b.kblocked:
-            Bm = _mat(b.ptr, (b.K // 64) * b.N, 64, 64).view(b.K // 64, b.N, 64).permute(1, 0, 2).reshape(b.N, b.K)
-        else:
-            Bm = _mat(b.ptr, b.N, b.K, b.ld)
-        lo, hi = (e[7], e[8]) if (len(e) > 7 and e[8]) else (0, N)
-        Bm = Bm[lo:hi, e[6]:e[6] + kk].float()
-        acc[:rows, lo:hi] += A @ Bm.t()
-    assert out.dtype == BF16 and out.shape == (M, N)
-    out.copy_(acc.to(BF16))
-    return out
+from gemm_interp import BF16, build_net, interp_gemm as _interp_gemm
 
 
 @pytest.mark.parametrize("cfg_name", ["TINY", "TINY_XL"])
 @pytest.mark.parametrize("lora_rows", [None, 1])
 def test_context_chunks_equal_per_layer_projections(monkeypatch, cfg_name, lora_rows):
-    from pcm_b200 import config, ops, weights
+    from pcm_b200 import config, ops
     from pcm_b200.unet import UNetB200
     cfg = getattr(config, cfg_name)
-    sd = weights.synthetic_state_dict(cfg, 3, lora_b_std=0.2)
-    old = ops.DRY_RUN
-    ops.DRY_RUN = []                       # construction only records (the LoRA refresh kernel)
-    try:
-        net = UNetB200(cfg, sd, "cpu", lora=True, need_backward=True)
-    finally:
-        ops.DRY_RUN = old
+    net, sd = build_net(cfg)
     assert net.ctx_group is not None and len(net.ctx_group.chunks) >= 1
     r, s = net.r, net.scale
-    # what pcm_lora_refresh writes: bf16 A and s*B copies through the per-layer views
-    for L in net.lora_layers:
-        lo = L.lora
-        na, nb = lo.a_fwd.numel(), lo.sb_fwd.numel()
-        A = net.lora_master[lo.a_off:lo.a_off + na].view_as(lo.a_fwd)
-        Bm = net.lora_master[lo.b_off:lo.b_off + nb].view_as(lo.sb_fwd)
-        lo.a_fwd.copy_(A.to(BF16))
-        lo.sb_fwd.copy_((s * Bm).to(BF16))
     B, S = 3, 77
     ctx = torch.randn(B * S, cfg.cross_attention_dim, generator=torch.Generator().manual_seed(5)).to(BF16)
     net._lb = (lora_rows or B, B)

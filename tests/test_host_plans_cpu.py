@@ -1,0 +1,212 @@
+"""HOST launch plans of the LoRA-fused Linear layers, checked on CPU by interpreting the `pcm_gemm`
+descriptors they build (tests/gemm_interp.py) against the peft definition
+    y = x W^T + b + s (x A^T) B^T
+(train_pcm_lora_sd15.py:868-885 wraps these modules with get_peft_model).
+
+Covers the plans the CUDA kernels cannot check by themselves: which stacked operand rows / columns a
+layer's LoRA K block reads, the N ranges of grouped layers, the adapter-on-leading-rows layout of the merged
+student + teacher pass, the residual / bias epilogue arguments.  (The kernels behind the same descriptors are
+compared with torch on the GPU in tests/test_gemm_gpu.py; the whole network against the oracle in
+tests/test_unet_gpu.py and tests/test_parity_gpu.py.)"""
+import pytest
+import torch
+
+from gemm_interp import BF16, build_net, interp_gemm, interp_wgrad as interp_wgrad_, lora_linear_ref
+
+
+@pytest.fixture(scope="module")
+def tiny():
+    from pcm_b200 import config
+    return build_net(config.TINY)
+
+
+def _close(got, ref, what):
+    err = (got.float() - ref).abs().max().item()
+    assert err <= 1.2e-2 * ref.abs().max().item() + 1e-3, (what, err)
+
+
+def _x(rows, cols, seed):
+    return torch.randn(rows, cols, generator=torch.Generator().manual_seed(seed)).to(BF16)
+
+
+@pytest.mark.parametrize("lora_rows", [None, 128])
+def test_linear_with_fused_lora_residual_and_bias(monkeypatch, tiny, lora_rows):
+    """attn1.to_out.0 (bias, residual) and ff.net.2: T = x A^T as its own launch on the adapter rows, then
+    one GEMM with the LoRA block as an extra K entry."""
+    from pcm_b200 import ops
+    net, sd = tiny
+    monkeypatch.setattr(ops, "gemm", interp_gemm)
+    M = 384
+    net._lb = (lora_rows or M, M)
+    for name in ("down_blocks.0.attentions.0.transformer_blocks.0.attn1.to_out.0",
+                 "down_blocks.1.attentions.1.transformer_blocks.0.ff.net.2",
+                 "mid_block.attentions.0.proj_in"):
+        L = net.layers[name]
+        x, res = _x(M, L.cin, 1), _x(M, L.cout, 2)
+        tape = []
+        y = net.linear(name, [x], True, residual=res, save=tape)
+        ref = lora_linear_ref(sd, name, x, net.scale, lora_rows) + res.float()
+        _close(y, ref, name)
+        (_, nm, xs, T), = tape
+        assert nm == name and T.shape == ((lora_rows or M), net.r) and xs[0].shape[0] == (lora_rows or M)
+        # without the adapter: the frozen layer
+        y0 = net.linear(name, [x], False)
+        W = sd[name + ".weight"].reshape(L.cout, -1).to(BF16).float()
+        _close(y0, x.float() @ W.t() + sd[name + ".bias"].float(), name + " base")
+        assert (y.float() - res.float() - y0.float())[: (lora_rows or M)].abs().max() > 1e-2   # the adapter is live
+
+
+def test_linear_over_channel_concatenated_sources(monkeypatch, tiny):
+    """conv_shortcut of an up-block resnet: two A sources (hidden state, skip) = torch.cat along channels."""
+    from pcm_b200 import ops
+    net, sd = tiny
+    monkeypatch.setattr(ops, "gemm", interp_gemm)
+    name = "up_blocks.1.resnets.0.conv_shortcut"
+    L = net.layers[name]
+    c1 = L.cin // 2
+    M = 256
+    net._lb = (M, M)
+    xa, xb = _x(M, c1, 3), _x(M, L.cin - c1, 4)
+    y = net.linear(name, [xa, xb], True)
+    _close(y, lora_linear_ref(sd, name, torch.cat([xa, xb], 1), net.scale), name)
+
+
+@pytest.mark.parametrize("lora_rows", [None, 128])
+def test_qkv_group_is_three_lora_linears(monkeypatch, tiny, lora_rows):
+    from pcm_b200 import ops
+    net, sd = tiny
+    monkeypatch.setattr(ops, "gemm", interp_gemm)
+    t = "down_blocks.1.attentions.0.transformer_blocks.0"
+    G = net.groups[t + ".attn1.to_q"]
+    M = 384
+    net._lb = (lora_rows or M, M)
+    x = _x(M, G.cin, 7)
+    tape = []
+    q, k, v = net.linear_group(t + ".attn1.to_q", x, True, save=tape)
+    for suf, got in ((".attn1.to_q", q), (".attn1.to_k", k), (".attn1.to_v", v)):
+        _close(got, lora_linear_ref(sd, t + suf, x, net.scale, lora_rows), t + suf)
+    assert q.stride(0) == 3 * G.cout and tape[0][3].shape == ((lora_rows or M), 3 * net.r)
+
+
+@pytest.mark.parametrize("lora_rows", [None, 1])
+def test_time_embedding_projections_as_one_group(monkeypatch, tiny, lora_rows):
+    """All resnets' time_emb_proj(silu(temb)) from ONE grouped launch: column range i == layer i."""
+    from pcm_b200 import ops
+    net, sd = tiny
+    monkeypatch.setattr(ops, "gemm", interp_gemm)
+    G = net.temb_group
+    assert G is not None and G.g == len([n for n in net.layers if n.endswith(".time_emb_proj")])
+    B = 3
+    net._lb = (lora_rows or B, B)
+    st = _x(B, G.cin, 9)
+    out, T = net.temb_all(st, True)
+    assert T.shape == ((lora_rows or B), G.g * net.r)
+    for i, name in enumerate(G.names):
+        _close(out[:, G.offs[i]:G.offs[i + 1]], lora_linear_ref(sd, name, st, net.scale, lora_rows), name)
+
+
+def test_frozen_weight_copies_equal_the_state_dict(tiny):
+    """Every Linear / 1x1 weight the plans read (K-blocked or stacked) is the state-dict tensor in bf16."""
+    from gemm_interp import b_matrix
+    from pcm_b200 import ops
+    net, sd = tiny
+    checked = 0
+    for name, L in net.layers.items():
+        if L.kind in ("gn", "ln") or L.w_fwd is None or L.kind == "conv" and L.k == 3:
+            continue
+        W = sd[name + ".weight"].reshape(L.cout, -1).to(BF16)
+        assert torch.equal(b_matrix(ops.bsrc(L.w_fwd)), W), name
+        checked += 1
+    for lead, G in net.groups.items():
+        Wg = torch.cat([sd[n + ".weight"] for n in G.names], 0).to(BF16)
+        assert torch.equal(b_matrix(ops.bsrc(G.w_stack)), Wg), lead
+        checked += 1
+    assert checked > 40
+
+
+def _autograd_ref(sd, names, x, dys, scale, lora_rows):
+    """float64 autograd through  y_i = x W_i^T + s (x A_i^T) B_i^T  (bf16-rounded parameters; adapter on
+    the leading rows): returns dx and {name: (dA, dB)}."""
+    x64 = x.double().requires_grad_(True)
+    params, loss = {}, 0.0
+    rows = x.shape[0] if lora_rows is None else lora_rows
+    for name, dy in zip(names, dys):
+        W = sd[name + ".weight"]
+        W = W.reshape(W.shape[0], -1).to(BF16).double()
+        A = sd[name + ".lora_A.weight"]
+        A = A.reshape(A.shape[0], -1).to(BF16).double().requires_grad_(True)
+        Bm = sd[name + ".lora_B.weight"]
+        Bm = Bm.reshape(Bm.shape[0], -1).to(BF16).double().requires_grad_(True)
+        y = x64 @ W.t()
+        y = torch.cat([y[:rows] + scale * (x64[:rows] @ A.t()) @ Bm.t(), y[rows:]], 0)
+        loss = loss + (y[:dy.shape[0]] * dy.double()).sum()
+        params[name] = (A, Bm)
+    loss.backward()
+    return x64.grad, {n: (a.grad, b.grad) for n, (a, b) in params.items()}
+
+
+def _rel(got, ref):
+    return ((got.double() - ref).norm() / (ref.norm() + 1e-30)).item()
+
+
+def test_linear_backward_plan(monkeypatch, tiny):
+    """linear_bwd: dt = dy (sB), dx = [dy | dt] [W ; A], and the two LoRA weight-gradient launches land in the
+    layer's slices of the flat gradient buffer."""
+    from pcm_b200 import ops
+    net, sd = tiny
+    monkeypatch.setattr(ops, "gemm", interp_gemm)
+    monkeypatch.setattr(ops, "wgrad", interp_wgrad_)
+    name = "down_blocks.1.attentions.1.transformer_blocks.0.ff.net.2"
+    L = net.layers[name]
+    M = 256
+    net._lb = (M, M)
+    x, dy = _x(M, L.cin, 11), _x(M, L.cout, 12)
+    tape = []
+    net.linear(name, [x], True, save=tape)
+    net.lora_grad.zero_()
+    dx = net.linear_bwd(tape[0], dy)
+    dx_ref, g = _autograd_ref(sd, [name], x, [dy], net.scale, None)
+    assert _rel(dx, dx_ref) < 1e-2
+    dA, dB = g[name]
+    assert _rel(L.lora.gA, dA) < 1e-2 and _rel(L.lora.gB, dB) < 1e-2
+    # nothing outside this layer's slices of the flat buffer was touched
+    lo = L.lora
+    mask = torch.ones_like(net.lora_grad, dtype=torch.bool)
+    mask[lo.a_off:lo.a_off + lo.gA.numel()] = False
+    mask[lo.b_off:lo.b_off + lo.gB.numel()] = False
+    assert not net.lora_grad[mask].any()
+
+
+@pytest.mark.parametrize("lead,need_dx", [(".attn1.to_q", True), (".attn2.to_k", False)])
+def test_grouped_backward_plan(monkeypatch, tiny, lead, need_dx):
+    """linear_group_bwd over the packed output gradients [dq | dk | dv] (resp. [dk | dv], no input gradient:
+    the text context is not trained), with T a column window of a wider stacked down-projection."""
+    from pcm_b200 import ops
+    net, sd = tiny
+    monkeypatch.setattr(ops, "gemm", interp_gemm)
+    monkeypatch.setattr(ops, "wgrad", interp_wgrad_)
+    t = "down_blocks.1.attentions.0.transformer_blocks.0"
+    G = net.groups[t + lead]
+    M = 154 if not need_dx else 256
+    net._lb = (M, M)
+    x = _x(M, G.cin, 13)
+    dys = [_x(M, G.cout, 20 + i) for i in range(G.g)]
+    dpk = torch.cat(dys, 1).contiguous()
+    if need_dx:
+        tape = []
+        net.linear_group(t + lead, x, True, save=tape)
+        rec = tape[0]
+    else:
+        kv = net.ctx_kv_all(x, True)            # T = this block's window of the stacked context projection
+        rec = ("lgroup", t + lead, x, kv[t][2])
+        assert rec[3].stride(0) == net.ctx_group.nl * net.r
+    net.lora_grad.zero_()
+    dx = net.linear_group_bwd(rec, dpk, need_dx=need_dx)
+    dx_ref, g = _autograd_ref(sd, G.names, x, dys, net.scale, None)
+    if need_dx:
+        assert _rel(dx, dx_ref) < 1e-2
+    else:
+        assert dx is None
+    for n in G.names:
+        lo = net.layers[n].lora
+        assert _rel(lo.gA, g[n][0]) < 1e-2 and _rel(lo.gB, g[n][1]) < 1e-2, n
