@@ -210,3 +210,95 @@ def test_grouped_backward_plan(monkeypatch, tiny, lead, need_dx):
     for n in G.names:
         lo = net.layers[n].lora
         assert _rel(lo.gA, g[n][0]) < 1e-2 and _rel(lo.gB, g[n][1]) < 1e-2, n
+
+
+# ---------------------------------------------------------------------------------------------
+# 3x3 convolutions: implicit-GEMM K programs (taps, skip concat, stride-2 parity planes) + LoRA
+# ---------------------------------------------------------------------------------------------
+def _conv_ref(sd, name, x_nchw, scale, stride, lora_samples=None, dtype=torch.float64):
+    """peft LoRA Conv2d on bf16-rounded parameters: conv(x, W) + b + s * B(A(x)), A = k x k conv with the
+    layer's stride / padding, B = 1x1; adapter on the leading samples only."""
+    F = torch.nn.functional
+    W = sd[name + ".weight"].to(BF16).to(dtype)
+    b = sd[name + ".bias"].to(dtype)
+    A = sd[name + ".lora_A.weight"].to(BF16).to(dtype)
+    Bm = sd[name + ".lora_B.weight"].to(BF16).to(dtype)
+    y = F.conv2d(x_nchw, W, b, stride=stride, padding=1)
+    n = x_nchw.shape[0] if lora_samples is None else lora_samples
+    ad = scale * F.conv2d(F.conv2d(x_nchw[:n], A, None, stride=stride, padding=1), Bm)
+    return torch.cat([y[:n] + ad, y[n:]], 0), (A, Bm)
+
+
+def _nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def _img(b, c, h, w, seed):
+    return torch.randn(b, c, h, w, generator=torch.Generator().manual_seed(seed)).to(BF16)
+
+
+@pytest.mark.parametrize("lora_samples", [None, 1])
+def test_resnet_conv_over_skip_concat_with_row_vector_and_residual(monkeypatch, tiny, lora_samples):
+    from pcm_b200 import ops
+    net, sd = tiny
+    monkeypatch.setattr(ops, "gemm", interp_gemm)
+    name = "up_blocks.1.resnets.0.conv1"          # input = cat(hidden, skip)
+    L = net.layers[name]
+    B, H, W = 3, 8, 8
+    net._lb = (lora_samples or B, B)
+    c1 = L.cin // 2
+    xa, xb = _img(B, c1, H, W, 31), _img(B, L.cin - c1, H, W, 32)
+    rv = _x(B, L.cout, 33)
+    res = _img(B, L.cout, H, W, 34)
+    tape = []
+    y = net.conv3(name, [_nhwc(xa), _nhwc(xb)], True, rowvec=rv, residual=_nhwc(res), save=tape)
+    ref, _ = _conv_ref(sd, name, torch.cat([xa, xb], 1).double(), net.scale, 1, lora_samples)
+    ref = ref + rv.double()[:, :, None, None] + res.double()
+    assert _rel(y.permute(0, 3, 1, 2), ref) < 6e-3
+    assert tape[0][3].shape == ((lora_samples or B), H, W, net.r)
+
+
+def test_downsample_conv_reads_the_four_parity_planes(monkeypatch, tiny):
+    from pcm_b200 import ops
+    net, sd = tiny
+    monkeypatch.setattr(ops, "gemm", interp_gemm)
+    name = "down_blocks.0.downsamplers.0.conv"
+    L = net.layers[name]
+    B, H, W = 2, 8, 8
+    net._lb = (B, B)
+    x = _img(B, L.cin, H, W, 35)
+    y = net.conv3(name, [_nhwc(x)], True, stride=2)
+    ref, _ = _conv_ref(sd, name, x.double(), net.scale, 2)
+    assert y.shape == (B, H // 2, W // 2, L.cout) and _rel(y.permute(0, 3, 1, 2), ref) < 6e-3
+
+
+@pytest.mark.parametrize("name,stride", [("down_blocks.1.resnets.0.conv2", 1), ("down_blocks.0.downsamplers.0.conv", 2)])
+def test_conv_backward_plan(monkeypatch, tiny, name, stride):
+    """conv3_bwd: dgrad over flipped taps (stride 2: one launch per parity plane of dx, written through a
+    strided view), dt = dy (sB), and the tap-wise LoRA weight gradients - against float64 autograd."""
+    from pcm_b200 import ops
+    net, sd = tiny
+    monkeypatch.setattr(ops, "gemm", interp_gemm)
+    monkeypatch.setattr(ops, "wgrad", interp_wgrad_)
+    L = net.layers[name]
+    B, H, W = 2, 8, 8
+    net._lb = (B, B)
+    x = _img(B, L.cin, H, W, 41)
+    dy = _img(B, L.cout, H // stride, W // stride, 42)
+    tape = []
+    net.conv3(name, [_nhwc(x)], True, stride=stride, save=tape)
+    net.lora_grad.zero_()
+    dx = net.conv3_bwd(tape[0], _nhwc(dy))
+    x64 = x.double().requires_grad_(True)
+    F = torch.nn.functional
+    Wt = sd[name + ".weight"].to(BF16).double()
+    A = sd[name + ".lora_A.weight"].to(BF16).double().requires_grad_(True)
+    Bm = sd[name + ".lora_B.weight"].to(BF16).double().requires_grad_(True)
+    y = (F.conv2d(x64, Wt, None, stride=stride, padding=1) +
+         net.scale * F.conv2d(F.conv2d(x64, A, None, stride=stride, padding=1), Bm))
+    (y * dy.double()).sum().backward()
+    assert _rel(dx.permute(0, 3, 1, 2), x64.grad) < 1e-2
+    lo = L.lora
+    gA = lo.gA.view(net.r, 3, 3, L.cin).permute(0, 3, 1, 2)        # [r, (kh, kw, cin)] -> [r, cin, kh, kw]
+    assert _rel(gA, A.grad) < 1e-2
+    assert _rel(lo.gB, Bm.grad.reshape(L.cout, net.r)) < 1e-2
