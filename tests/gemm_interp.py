@@ -107,12 +107,13 @@ def interp_wgrad(p_src, q_src, out, *, lin, M, os_row, os_col, alpha=1.0, q_c0=0
     return out
 
 
-def build_net(cfg, seed=3, lora_b_std=0.2):
+def build_net(cfg, seed=3, lora_b_std=0.2, sd=None):
     """UNetB200 on CPU in record-only mode, with the operand copies `pcm_lora_refresh` would write
     (bf16 A and s*B through the per-layer views)."""
     from pcm_b200 import ops, weights
     from pcm_b200.unet import UNetB200
-    sd = weights.synthetic_state_dict(cfg, seed, lora_b_std=lora_b_std)
+    if sd is None:
+        sd = weights.synthetic_state_dict(cfg, seed, lora_b_std=lora_b_std)
     old = ops.DRY_RUN
     ops.DRY_RUN = []
     try:

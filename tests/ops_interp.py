@@ -1,0 +1,165 @@
+"""Test-side torch semantics of every `pcm_b200.ops` wrapper the UNet sequencing code calls, so that the
+HOST logic of pcm_b200/unet.py (tape, backward walk, merged student + teacher pass, grouped layers,
+gradient buffer layout) can be executed and compared with the oracle on CPU.
+
+`install(monkeypatch)` replaces the wrappers in `pcm_b200.ops` for the duration of one test.  The
+semantics follow include/pcm_b200.h (the same statements the GPU tests check the CUDA kernels against,
+tests/test_ops_gpu.py / test_gemm_gpu.py / test_attn_gpu.py).  Test infrastructure only: nothing under
+pcm_b200/ imports this file, and the product raises when libpcm_b200.so is missing."""
+import math
+
+import torch
+
+from gemm_interp import BF16, interp_gemm, interp_wgrad
+
+F = torch.nn.functional
+
+
+def _gn(x, B, HW, G, gamma, beta, eps, silu):
+    C = x.shape[-1]
+    xg = x.view(B, HW, G, C // G)
+    mean = xg.mean(dim=(1, 3), keepdim=True)
+    var = xg.var(dim=(1, 3), unbiased=False, keepdim=True)
+    rstd = (var + eps).rsqrt()
+    y = ((xg - mean) * rstd).view(B * HW, C) * gamma + beta
+    return (F.silu(y) if silu else y), mean.view(B, G), rstd.view(B, G)
+
+
+def _cat(x1, x2):
+    return x1.float() if x2 is None else torch.cat([x1.float(), x2.float()], -1)
+
+
+def groupnorm_fwd(x1, x2, gamma, beta, eps, silu, out, stats, B, HW, G=32):
+    y, mean, rstd = _gn(_cat(x1, x2), B, HW, G, gamma, beta, eps, silu)
+    out.copy_(y.to(out.dtype))
+    stats.copy_(torch.stack([mean, rstd], -1))
+    return out
+
+
+def groupnorm_bwd(dy, x1, x2, gamma, beta, eps, silu, stats, red, add, dx1, dx2, B, HW, G=32, colsum=None):
+    x = _cat(x1, x2).requires_grad_(True)
+    with torch.enable_grad():
+        y, _, _ = _gn(x, B, HW, G, gamma, beta, eps, silu)
+        (y * dy.float()).sum().backward()
+    dx = x.grad
+    if add is not None:
+        dx = dx + add.float().reshape(dx.shape)
+    if colsum is not None:
+        colsum.copy_(dx.view(B, HW, -1).sum(1))
+    C1 = x1.shape[-1]
+    dx1.copy_(dx[:, :C1].to(dx1.dtype))
+    if dx2 is not None:
+        dx2.copy_(dx[:, C1:].to(dx2.dtype))
+
+
+def layernorm_fwd(x, gamma, beta, out, stats, eps=1e-5):
+    xf = x.float()
+    mean = xf.mean(-1, keepdim=True)
+    rstd = (xf.var(-1, unbiased=False, keepdim=True) + eps).rsqrt()
+    out.copy_(((xf - mean) * rstd * gamma + beta).to(out.dtype))
+    stats.copy_(torch.cat([mean, rstd], -1))
+    return out
+
+
+def layernorm_bwd(dy, x, gamma, stats, add, dx):
+    xf = x.float().requires_grad_(True)
+    with torch.enable_grad():
+        y = F.layer_norm(xf, (xf.shape[-1],), gamma, None, 1e-5)
+        (y * dy.float()).sum().backward()
+    g = xf.grad if add is None else xf.grad + add.float()
+    dx.copy_(g.to(dx.dtype))
+    return dx
+
+
+def _heads(t, B, S, H, D):
+    return t[:, :H * D].float().reshape(B, S, H, D).permute(0, 2, 1, 3)
+
+
+def attn_fwd(q, k, v, out, lse, B, H, Sq, Skv, D, scale):
+    Q, K, V = _heads(q, B, Sq, H, D), _heads(k, B, Skv, H, D), _heads(v, B, Skv, H, D)
+    s = (Q @ K.transpose(-1, -2)) * scale
+    lse.copy_(torch.logsumexp(s, -1))
+    o = torch.softmax(s, -1) @ V
+    out[:, :H * D].copy_(o.permute(0, 2, 1, 3).reshape(B * Sq, H * D).to(out.dtype))
+    return out
+
+
+def attn_bwd(q, k, v, o, dout, lse, delta, dq, dk, dv, B, H, Sq, Skv, D, scale):
+    assert o.stride(0) == dout.stride(0) and dq.stride(0) == q.stride(0)
+    assert dk.stride(0) == k.stride(0) and dv.stride(0) == v.stride(0)
+    Q = _heads(q, B, Sq, H, D).requires_grad_(True)
+    K = _heads(k, B, Skv, H, D).requires_grad_(True)
+    V = _heads(v, B, Skv, H, D).requires_grad_(True)
+    with torch.enable_grad():
+        out = torch.softmax((Q @ K.transpose(-1, -2)) * scale, -1) @ V
+        (out * _heads(dout, B, Sq, H, D)).sum().backward()
+    for dst, g, S in ((dq, Q.grad, Sq), (dk, K.grad, Skv), (dv, V.grad, Skv)):
+        dst[:, :H * D].copy_(g.permute(0, 2, 1, 3).reshape(B * S, H * D).to(dst.dtype))
+
+
+def geglu_fwd(u, out):
+    Fh = u.shape[1] // 2
+    uf = u.float()
+    out.copy_((uf[:, :Fh] * F.gelu(uf[:, Fh:])).to(out.dtype))     # diffusers GEGLU: hidden * gelu(gate), exact erf
+    return out
+
+
+def geglu_bwd(dgg, u, du):
+    Fh = u.shape[1] // 2
+    uf = u.float().requires_grad_(True)
+    with torch.enable_grad():
+        ((uf[:, :Fh] * F.gelu(uf[:, Fh:])) * dgg.float()).sum().backward()
+    du.copy_(uf.grad.to(du.dtype))
+    return du
+
+
+def upsample2x_fwd(x, out):
+    out.copy_(x.repeat_interleave(2, 1).repeat_interleave(2, 2))
+    return out
+
+
+def upsample2x_bwd(dout, din):
+    B, H, W, C = din.shape
+    din.copy_(dout.float().view(B, H, 2, W, 2, C).sum((2, 4)).to(din.dtype))
+    return din
+
+
+def conv3x3_c4(x, w, bias, out, sgn=1, round_in=True):
+    """4-channel edge convolutions: out[b,h,w,c] = sum_taps x[b, h+sgn*dh, w+sgn*dw, :] . w[c, kh, kw, :]."""
+    xf = x.to(BF16).float() if round_in else x.float()
+    wt = w.float().permute(0, 3, 1, 2)                 # [C, 4, 3, 3]
+    if sgn < 0:
+        wt = wt.flip(2, 3)
+    y = F.conv2d(xf.permute(0, 3, 1, 2), wt, None if bias is None else bias.float(), padding=1)
+    out.copy_(y.permute(0, 2, 3, 1).to(out.dtype))
+    return out
+
+
+def timestep_embed(t, out):
+    """diffusers Timesteps(flip_sin_to_cos=True, downscale_freq_shift=0): [cos | sin]."""
+    half = out.shape[1] // 2
+    f = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32) / half)
+    a = t.float().reshape(-1, 1) * f
+    out.copy_(torch.cat([a.cos(), a.sin()], -1).to(out.dtype))
+    return out
+
+
+def cast_f32_bf16(x, out):
+    out.copy_(x.to(BF16).view(out.shape))
+    return out
+
+
+def add_bf16(a, b, out):
+    out.copy_((a.float() + b.float()).to(out.dtype))
+    return out
+
+
+def install(monkeypatch):
+    from pcm_b200 import ops
+    g = globals()
+    for name in ("groupnorm_fwd", "groupnorm_bwd", "layernorm_fwd", "layernorm_bwd", "attn_fwd", "attn_bwd",
+                 "geglu_fwd", "geglu_bwd", "upsample2x_fwd", "upsample2x_bwd", "conv3x3_c4", "timestep_embed",
+                 "cast_f32_bf16", "add_bf16"):
+        monkeypatch.setattr(ops, name, g[name])
+    monkeypatch.setattr(ops, "gemm", interp_gemm)
+    monkeypatch.setattr(ops, "wgrad", interp_wgrad)

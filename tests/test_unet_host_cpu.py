@@ -1,0 +1,98 @@
+"""HOST logic of pcm_b200/unet.py executed on CPU: every `ops` wrapper is replaced by its torch semantics
+(tests/ops_interp.py, tests/gemm_interp.py - descriptors interpreted through their raw pointers), the
+sequencing code itself (tape, backward walk, grouped layers, context chunks, merged student + teacher
+pass, flat gradient buffer) is the product's.  Compared with the oracle network (oracle/unet_ref.py) on
+identical seeded weights - the CPU twin of tests/test_unet_gpu.py (which checks the same with the CUDA
+kernels behind the wrappers)."""
+import pytest
+import torch
+
+import ops_interp
+from gemm_interp import BF16, build_net
+
+
+def _nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def _nchw(x):
+    return x.permute(0, 3, 1, 2).contiguous()
+
+
+def _setup(cfg_name, B, hw, seed=0):
+    from oracle import pcm_ref, unet_ref
+    from pcm_b200 import config
+    ocfg = getattr(unet_ref, cfg_name)
+    P = unet_ref.init_params(ocfg, seed, lora_b_std=0.02)
+    batch = pcm_ref.make_batch(ocfg, B, hw, seed=seed)
+    net, _ = build_net(getattr(config, cfg_name), sd=P)
+    return ocfg, P, batch, net
+
+
+def _added(ocfg, batch, B):
+    if not getattr(ocfg, "addition_embed", False):
+        return None, None
+    return (batch["text_embeds"], batch["time_ids"]), dict(text_embeds=batch["text_embeds"], time_ids=batch["time_ids"])
+
+
+@pytest.mark.parametrize("cfg_name", ["TINY", "TINY_XL"])
+def test_forward_and_backward_match_the_oracle(monkeypatch, cfg_name):
+    from oracle import unet_ref
+    B, hw = 2, 8
+    ocfg, P, batch, net = _setup(cfg_name, B, hw)
+    ops_interp.install(monkeypatch)
+    x, ctx = batch["latents"], batch["prompt_embeds"]
+    ts = torch.tensor([999, 19])
+    added, okw = _added(ocfg, batch, B)
+    kw = {} if okw is None else dict(added_cond_kwargs=okw)
+    ctx2 = ctx.to(BF16).reshape(B * ctx.shape[1], -1)
+    for lora in (True, False):
+        ref = unet_ref.UNetRef(ocfg, P, use_lora=lora, emulate_bf16=True)(x, ts, ctx, **kw)
+        out = _nchw(net.forward(_nhwc(x), ts, ctx2, lora=lora, added_cond=added))
+        err = (out - ref).abs()
+        assert err.max().item() <= 3e-2 * ref.abs().max().item(), (lora, err.max().item())
+        assert err.mean().item() <= 1e-2 * ref.pow(2).mean().sqrt().item(), (lora, err.mean().item())
+    # backward: LoRA gradients of sum(eps * G)
+    G = torch.randn(B, 4, hw, hw, generator=torch.Generator().manual_seed(7)) / (B * 4 * hw * hw)
+    Pg = {k: (v.clone().requires_grad_(True) if ".lora_" in k else v) for k, v in P.items()}
+    eps = unet_ref.UNetRef(ocfg, Pg, use_lora=True, emulate_bf16=True)(x, ts, ctx, **kw)
+    (eps * G).sum().backward()
+    net.forward(_nhwc(x), ts, ctx2, lora=True, save=True, added_cond=added)
+    net.lora_grad.zero_()
+    net.backward(_nhwc(G))
+    g = net.lora_grad_dict()
+    num = den = 0.0
+    for k, v in Pg.items():
+        if ".lora_" in k:
+            num += (g[k].float() - v.grad.reshape(g[k].shape)).pow(2).sum().item()
+            den += v.grad.pow(2).sum().item()
+    assert (num / den) ** 0.5 <= 5e-2, (num / den) ** 0.5
+
+
+def test_merged_pass_is_student_plus_frozen_teacher(monkeypatch):
+    """lora_batch = b < B: the leading b samples see the adapter, the others the frozen network, in ONE
+    pass; the tape then belongs to the student samples and backward() gives the student's gradients."""
+    B, hw = 3, 8
+    ocfg, P, batch, net = _setup("TINY", B, hw)
+    ops_interp.install(monkeypatch)
+    x, ctx = _nhwc(batch["latents"]), batch["prompt_embeds"].to(BF16)
+    S = ctx.shape[1]
+    ctx2 = ctx.reshape(B * S, -1)
+    ts = torch.tensor([999, 19, 499])
+    merged = net.forward(x, ts, ctx2, lora=True, save=True, lora_batch=1)
+    kv = net.last_ctx_kv
+    G = torch.randn(1, hw, hw, 4, generator=torch.Generator().manual_seed(8)) / (4 * hw * hw)
+    net.lora_grad.zero_()
+    net.backward(G)
+    g_merged = net.lora_grad.clone()
+    stu = net.forward(x[:1], ts[:1], ctx2[:S], lora=True, save=True)
+    net.lora_grad.zero_()
+    net.backward(G)
+    tea = net.forward(x[1:], ts[1:], ctx2[S:], lora=False)
+    assert torch.equal(merged[:1], stu) and torch.equal(merged[1:], tea)
+    # (same launches on the same student rows; torch's CPU matmul blocking may differ in the last bit)
+    assert ((g_merged - net.lora_grad).norm() / net.lora_grad.norm()).item() < 1e-5 and g_merged.abs().max() > 0
+    # the target pass of the step takes the student rows of the merged pass's context projections
+    sub = net.ctx_kv_rows(kv, S)
+    again = net.forward(x[:1], ts[:1], ctx2[:S], lora=True, ctx_kv=sub)
+    assert torch.equal(again, stu)
