@@ -163,3 +163,100 @@ def install(monkeypatch):
         monkeypatch.setattr(ops, name, g[name])
     monkeypatch.setattr(ops, "gemm", interp_gemm)
     monkeypatch.setattr(ops, "wgrad", interp_wgrad)
+
+
+# ---------------------------------------------------------------------------------------------
+# the fused PCM kernels behind ops._call (raw-pointer C ABI, include/pcm_b200.h): restated with the
+# pinned oracle functions (oracle/pcm_ref.py == train_pcm_lora_sd15.py:240-341 executed verbatim)
+# ---------------------------------------------------------------------------------------------
+import ctypes  # noqa: E402
+
+
+def _raw(ptr, n, ctype, dtype):
+    return torch.frombuffer((ctype * n).from_address(ptr), dtype=dtype)
+
+
+class PcmCalls:
+    """Stand-in for ops._call on CPU.  `coef` (the kernels' private [B,16] table) is not modelled: the
+    per-step quantities live in this object between pcm_prepare and the consumers."""
+
+    def __init__(self):
+        self.s = None
+
+    def __call__(self, name, *args):
+        fn = getattr(self, name, None)
+        if fn is None:
+            raise AssertionError(f"no CPU semantics for {name}")
+        return fn(*args)
+
+    def pcm_prepare(self, acp, num_train, num_ddim, inf_idx, multiphase, index, w, B, bf16_mode, coef,
+                    start_t, t, end_t):
+        from oracle import pcm_ref
+        ac = _raw(acp, num_train, ctypes.c_float, torch.float32).clone()
+        idx = _raw(index, B, ctypes.c_int64, torch.int64).clone()
+        wv = _raw(w, B, ctypes.c_float, torch.float32).clone()
+        solver = pcm_ref.DDIMSolverRef(ac.numpy(), num_train, num_ddim)
+        st = solver.ddim_timesteps[idx]
+        inf = torch.from_numpy(pcm_ref.inference_indices(num_ddim, multiphase)).long()
+        assert torch.equal(inf, _raw(inf_idx, multiphase, ctypes.c_int64, torch.int64))
+        p = inf[(idx[:, None] >= inf[None, :]).long().sum(1) - 1]
+        _raw(start_t, B, ctypes.c_int64, torch.int64).copy_(st)
+        _raw(t, B, ctypes.c_int64, torch.int64).copy_(torch.clamp(st - num_train // num_ddim, min=0))
+        _raw(end_t, B, ctypes.c_int64, torch.int64).copy_(solver.ddim_timesteps_prev[p])
+        self.s = dict(ac=ac, idx=idx, w=wv.to(BF16).float() if bf16_mode else wv, solver=solver, inf=inf,
+                      multiphase=multiphase, start_t=st, t=torch.clamp(st - num_train // num_ddim, min=0),
+                      alpha=torch.sqrt(ac), sigma=torch.sqrt(1 - ac))
+
+    def pcm_add_noise(self, x, noise, coef, per, B, bf16_mode, out):
+        from oracle import pcm_ref
+        s = self.s
+        xs = _raw(x, B * per, ctypes.c_float, torch.float32).view(B, per)
+        ns = _raw(noise, B * per, ctypes.c_float, torch.float32).view(B, per)
+        if bf16_mode:
+            y = pcm_ref.add_noise(s["ac"], xs.to(BF16), ns.to(BF16), s["start_t"]).float()
+        else:
+            y = pcm_ref.add_noise(s["ac"], xs, ns, s["start_t"])
+        _raw(out, B * per, ctypes.c_float, torch.float32).view(B, per).copy_(y)
+
+    def pcm_teacher_step(self, eps_c, eps_u, noisy, coef, per, B, pred_type, x_prev):
+        from oracle import pcm_ref
+        s = self.s
+        pt = "epsilon" if pred_type == 0 else "v_prediction"
+        f = lambda p: _raw(p, B * per, ctypes.c_float, torch.float32).view(B, per)  # noqa: E731
+        ec, eu, xn = f(eps_c), f(eps_u), f(noisy)
+        x0c = pcm_ref.predicted_origin(ec, s["start_t"], xn, pt, s["alpha"], s["sigma"])
+        x0u = pcm_ref.predicted_origin(eu, s["start_t"], xn, pt, s["alpha"], s["sigma"])
+        w4 = s["w"].reshape(-1, 1)
+        xp = s["solver"].ddim_step(x0c + w4 * (x0c - x0u), ec + w4 * (ec - eu), s["idx"])
+        f(x_prev).copy_(xp.float())
+
+    def pcm_loss(self, eps_s, eps_t, noisy, x_prev, coef, per, B, loss_type, huber_c, pred_type, loss_out,
+                 d_eps, model_pred, target):
+        from oracle import pcm_ref
+        s = self.s
+        pt = "epsilon" if pred_type == 0 else "v_prediction"
+        f = lambda p: _raw(p, B * per, ctypes.c_float, torch.float32).view(B, per)  # noqa: E731
+        es = f(eps_s).clone().requires_grad_(True)
+        et, xn, xp = f(eps_t), f(noisy), f(x_prev).double()
+        c_skip, c_out = [v.reshape(-1, 1) for v in pcm_ref.scalings_for_boundary_conditions_target(s["idx"], s["inf"])]
+        with torch.enable_grad():
+            x0 = pcm_ref.predicted_origin(es, s["start_t"], xn, pt, s["alpha"], s["sigma"])
+            mp, _ = s["solver"].ddim_style_multiphase_pred(x0, es, s["idx"], s["multiphase"])
+            x0t = pcm_ref.predicted_origin(et, s["t"], xp, pt, s["alpha"], s["sigma"])
+            tg, _ = s["solver"].ddim_style_multiphase_pred(x0t, et, s["idx"], s["multiphase"])
+            tg = c_skip * xp + c_out * tg
+            d = mp.float() - tg.float()
+            loss = (d ** 2).mean() if loss_type == 1 else (torch.sqrt(d ** 2 + huber_c ** 2) - huber_c).mean()
+            loss.backward()
+        _raw(loss_out, 1, ctypes.c_float, torch.float32).copy_(loss.detach().reshape(1))
+        f(d_eps).copy_(es.grad)
+        if model_pred:
+            f(model_pred).copy_(mp.detach().float())
+        if target:
+            f(target).copy_(tg.detach().float())
+
+
+def install_step(monkeypatch):
+    from pcm_b200 import ops
+    install(monkeypatch)
+    monkeypatch.setattr(ops, "_call", PcmCalls())

@@ -96,3 +96,61 @@ def test_merged_pass_is_student_plus_frozen_teacher(monkeypatch):
     sub = net.ctx_kv_rows(kv, S)
     again = net.forward(x[:1], ts[:1], ctx2[:S], lora=True, ctx_kv=sub)
     assert torch.equal(again, stu)
+
+
+@pytest.mark.parametrize("merge", ["1", "0"])
+def test_step_host_sequence_matches_the_oracle_iteration(monkeypatch, merge):
+    """PCMTrainStep.forward_backward on CPU (every kernel replaced by its torch semantics): merged student +
+    teacher pass, teacher DDIM step, target pass on the student's context projections, loss, backward -
+    vs oracle/pcm_ref.pcm_step_ref (T15:1139-1296).  CPU twin of
+    tests/test_unet_gpu.py::test_step_loss_and_grads_match_oracle."""
+    from oracle import pcm_ref, unet_ref
+    from pcm_b200 import config, ops
+    from pcm_b200.step import PCMTrainStep
+    monkeypatch.setenv("PCM_MERGE_PASSES", merge)
+    B, hw, multiphase = 2, 8, 4
+    ocfg = unet_ref.TINY
+    P = unet_ref.init_params(ocfg, 0, lora_b_std=0.02)
+    batch = pcm_ref.make_batch(ocfg, B, hw, seed=0)
+    ref = pcm_ref.pcm_step_ref(ocfg, P, batch, multiphase=multiphase, emulate_bf16=True, need_grad=True)
+    old = ops.DRY_RUN
+    ops.DRY_RUN = []
+    try:
+        st = PCMTrainStep(config.TINY, P, "cpu", batch=B, height=hw, width=hw, multiphase=multiphase,
+                          keep_debug=True)
+    finally:
+        ops.DRY_RUN = old
+    net = st.unet
+    for L in net.lora_layers:       # what pcm_lora_refresh writes
+        lo = L.lora
+        taps = L.k * L.k if L.kind == "conv" else 1
+        na, nb = lo.a_fwd.numel(), lo.sb_fwd.numel()
+        lo.a_fwd.copy_(net.lora_master[lo.a_off:lo.a_off + na].view_as(lo.a_fwd).to(BF16))
+        sB = (net.scale * net.lora_master[lo.b_off:lo.b_off + nb].view_as(lo.sb_fwd)).to(BF16)
+        lo.sb_fwd.copy_(sB)
+        lo.sb_t.copy_(sB.t())
+        lo.a_t.copy_(lo.a_fwd.view(net.r, taps, L.cin).permute(2, 1, 0).reshape(L.cin, taps * net.r))
+    ops_interp.install_step(monkeypatch)
+    st.load_inputs(_nhwc(batch["latents"]), _nhwc(batch["noise"]), batch["index"], batch["w"],
+                   batch["prompt_embeds"].to(BF16), batch["uncond_prompt_embeds"].to(BF16))
+    net.lora_grad.zero_()
+    st.forward_backward()
+    assert torch.equal(st.start_t, ref["start_timesteps"]) and torch.equal(st.t, ref["timesteps"])
+    assert torch.equal(st.end_t, ref["end_timesteps"])
+    rel = lambda a, b: ((a.double() - b.double()).norm() / b.double().norm()).item()  # noqa: E731
+    assert rel(_nchw(st.debug["eps_student"]), ref["eps_student"]) < 2e-2
+    assert rel(_nchw(st.x_prev), ref["x_prev"]) < 2e-2
+    assert rel(_nchw(st.model_pred), ref["model_pred"]) < 2e-2 and rel(_nchw(st.target), ref["target"]) < 2e-2
+    assert abs(st.loss.item() - ref["loss"].item()) <= 4e-2 * ref["loss"].item()
+    g = net.lora_grad_dict()
+    dot = n1 = n2 = 0.0
+    for k, rg in ref["grads"].items():
+        gg = g[k].float().reshape(rg.shape)
+        dot += (gg * rg).sum().item()
+        n1 += gg.pow(2).sum().item()
+        n2 += rg.pow(2).sum().item()
+    cos = dot / (n1 ** 0.5 * n2 ** 0.5)
+    print(f"[host step, merge={merge}] loss {st.loss.item():.6f} (oracle {ref['loss'].item():.6f}) | rel-L2 eps "
+          f"{rel(_nchw(st.debug['eps_student']), ref['eps_student']):.2e} x_prev {rel(_nchw(st.x_prev), ref['x_prev']):.2e} "
+          f"| LoRA-gradient cosine {cos:.4f}")
+    assert cos >= 0.85          # same bound as the GPU twin (Huber sign noise)
