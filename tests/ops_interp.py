@@ -230,6 +230,24 @@ class PcmCalls:
         xp = s["solver"].ddim_step(x0c + w4 * (x0c - x0u), ec + w4 * (ec - eu), s["idx"])
         f(x_prev).copy_(xp.float())
 
+    def pcm_teacher_substep(self, eps_c, eps_u, x_cur, acp, t_cur, t_next, coef, per, B, pred_type, x_next):
+        """one DDIM sub-step t_cur -> t_next of the CFG-mixed prediction (t_next < 0: the solver's
+        alpha_cumprods[0] entry), float64 like DDIMSolver.ddim_step"""
+        from oracle import pcm_ref
+        s = self.s
+        pt = "epsilon" if pred_type == 0 else "v_prediction"
+        f = lambda p: _raw(p, B * per, ctypes.c_float, torch.float32).view(B, per)  # noqa: E731
+        ec, eu, xc = f(eps_c), f(eps_u), f(x_cur)
+        tc = _raw(t_cur, B, ctypes.c_int64, torch.int64)
+        tn = _raw(t_next, B, ctypes.c_int64, torch.int64)
+        x0c = pcm_ref.predicted_origin(ec, tc, xc, pt, s["alpha"], s["sigma"])
+        x0u = pcm_ref.predicted_origin(eu, tc, xc, pt, s["alpha"], s["sigma"])
+        w4 = s["w"].reshape(-1, 1)
+        acd = s["ac"].double()
+        a_n = torch.where(tn < 0, acd[0], acd[tn.clamp(min=0)]).reshape(-1, 1)
+        xn = a_n.sqrt() * (x0c + w4 * (x0c - x0u)) + (1.0 - a_n).sqrt() * (ec + w4 * (ec - eu))
+        f(x_next).copy_(xn.float())
+
     def pcm_loss(self, eps_s, eps_t, noisy, x_prev, coef, per, B, loss_type, huber_c, pred_type, loss_out,
                  d_eps, model_pred, target):
         from oracle import pcm_ref

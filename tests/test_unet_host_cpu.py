@@ -98,8 +98,18 @@ def test_merged_pass_is_student_plus_frozen_teacher(monkeypatch):
     assert torch.equal(again, stu)
 
 
-@pytest.mark.parametrize("merge", ["1", "0"])
-def test_step_host_sequence_matches_the_oracle_iteration(monkeypatch, merge):
+VARIANTS = {
+    "reference": dict(),
+    "v_prediction_l2": dict(prediction_type="v_prediction", loss_type="l2"),
+    "no_cfg_solver": dict(apply_cfg_solver=False),
+    "two_substeps": dict(teacher_substeps=2),
+    "two_phases": dict(multiphase=2),
+}
+
+
+@pytest.mark.parametrize("merge,variant", [("1", "reference"), ("0", "reference"), ("1", "v_prediction_l2"),
+                                           ("1", "no_cfg_solver"), ("1", "two_substeps"), ("1", "two_phases")])
+def test_step_host_sequence_matches_the_oracle_iteration(monkeypatch, merge, variant):
     """PCMTrainStep.forward_backward on CPU (every kernel replaced by its torch semantics): merged student +
     teacher pass, teacher DDIM step, target pass on the student's context projections, loss, backward -
     vs oracle/pcm_ref.pcm_step_ref (T15:1139-1296).  CPU twin of
@@ -108,16 +118,17 @@ def test_step_host_sequence_matches_the_oracle_iteration(monkeypatch, merge):
     from pcm_b200 import config, ops
     from pcm_b200.step import PCMTrainStep
     monkeypatch.setenv("PCM_MERGE_PASSES", merge)
-    B, hw, multiphase = 2, 8, 4
+    kw = dict(VARIANTS[variant])
+    B, hw, multiphase = 2, 8, kw.pop("multiphase", 4)
     ocfg = unet_ref.TINY
     P = unet_ref.init_params(ocfg, 0, lora_b_std=0.02)
     batch = pcm_ref.make_batch(ocfg, B, hw, seed=0)
-    ref = pcm_ref.pcm_step_ref(ocfg, P, batch, multiphase=multiphase, emulate_bf16=True, need_grad=True)
+    ref = pcm_ref.pcm_step_ref(ocfg, P, batch, multiphase=multiphase, emulate_bf16=True, need_grad=True, **kw)
     old = ops.DRY_RUN
     ops.DRY_RUN = []
     try:
         st = PCMTrainStep(config.TINY, P, "cpu", batch=B, height=hw, width=hw, multiphase=multiphase,
-                          keep_debug=True)
+                          keep_debug=True, **kw)
     finally:
         ops.DRY_RUN = old
     net = st.unet
@@ -139,8 +150,12 @@ def test_step_host_sequence_matches_the_oracle_iteration(monkeypatch, merge):
     assert torch.equal(st.end_t, ref["end_timesteps"])
     rel = lambda a, b: ((a.double() - b.double()).norm() / b.double().norm()).item()  # noqa: E731
     assert rel(_nchw(st.debug["eps_student"]), ref["eps_student"]) < 2e-2
-    assert rel(_nchw(st.x_prev), ref["x_prev"]) < 2e-2
-    assert rel(_nchw(st.model_pred), ref["model_pred"]) < 2e-2 and rel(_nchw(st.target), ref["target"]) < 2e-2
+    # v_prediction: x_prev = sqrt(a')(a x - s v) + sqrt(1-a') v does not cancel the bf16 noise of the
+    # CFG-amplified teacher output the way the epsilon form does (the kernels themselves: 1e-6,
+    # tests/test_pcm_kernels_gpu.py)
+    tol = 1.5e-1 if kw.get("prediction_type") == "v_prediction" else 2e-2
+    assert rel(_nchw(st.x_prev), ref["x_prev"]) < tol
+    assert rel(_nchw(st.model_pred), ref["model_pred"]) < tol and rel(_nchw(st.target), ref["target"]) < tol
     assert abs(st.loss.item() - ref["loss"].item()) <= 4e-2 * ref["loss"].item()
     g = net.lora_grad_dict()
     dot = n1 = n2 = 0.0
@@ -150,7 +165,7 @@ def test_step_host_sequence_matches_the_oracle_iteration(monkeypatch, merge):
         n1 += gg.pow(2).sum().item()
         n2 += rg.pow(2).sum().item()
     cos = dot / (n1 ** 0.5 * n2 ** 0.5)
-    print(f"[host step, merge={merge}] loss {st.loss.item():.6f} (oracle {ref['loss'].item():.6f}) | rel-L2 eps "
+    print(f"[host step, merge={merge}, {variant}] loss {st.loss.item():.6f} (oracle {ref['loss'].item():.6f}) | rel-L2 eps "
           f"{rel(_nchw(st.debug['eps_student']), ref['eps_student']):.2e} x_prev {rel(_nchw(st.x_prev), ref['x_prev']):.2e} "
           f"| LoRA-gradient cosine {cos:.4f}")
     assert cos >= 0.85          # same bound as the GPU twin (Huber sign noise)
