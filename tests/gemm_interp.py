@@ -120,6 +120,13 @@ def build_net(cfg, seed=3, lora_b_std=0.2, sd=None):
         net = UNetB200(cfg, sd, "cpu", lora=True, need_backward=True)
     finally:
         ops.DRY_RUN = old
+    refresh_operands(net)
+    return net, sd
+
+
+def refresh_operands(net):
+    """What `pcm_lora_refresh` writes: the bf16 operand copies A, s*B, (s*B)^T and the per-tap A^T of every
+    LoRA layer, from the fp32 master buffer, through the per-layer views."""
     for L in net.lora_layers:
         lo = L.lora
         na, nb = lo.a_fwd.numel(), lo.sb_fwd.numel()
@@ -130,7 +137,6 @@ def build_net(cfg, seed=3, lora_b_std=0.2, sd=None):
         taps = L.k * L.k if L.kind == "conv" else 1
         # A^T per tap: a_t[c, t*r + j] = a_fwd[j, t*cin + c]  (the dgrad K program reads column block t)
         lo.a_t.copy_(lo.a_fwd.view(net.r, taps, L.cin).permute(2, 1, 0).reshape(L.cin, taps * net.r))
-    return net, sd
 
 
 def lora_linear_ref(sd, name, x, scale, lora_rows=None, bias=True):

@@ -8,7 +8,7 @@ import pytest
 import torch
 
 import ops_interp
-from gemm_interp import BF16, build_net
+from gemm_interp import BF16, build_net, refresh_operands
 
 
 def _nhwc(x):
@@ -132,15 +132,7 @@ def test_step_host_sequence_matches_the_oracle_iteration(monkeypatch, merge, var
     finally:
         ops.DRY_RUN = old
     net = st.unet
-    for L in net.lora_layers:       # what pcm_lora_refresh writes
-        lo = L.lora
-        taps = L.k * L.k if L.kind == "conv" else 1
-        na, nb = lo.a_fwd.numel(), lo.sb_fwd.numel()
-        lo.a_fwd.copy_(net.lora_master[lo.a_off:lo.a_off + na].view_as(lo.a_fwd).to(BF16))
-        sB = (net.scale * net.lora_master[lo.b_off:lo.b_off + nb].view_as(lo.sb_fwd)).to(BF16)
-        lo.sb_fwd.copy_(sB)
-        lo.sb_t.copy_(sB.t())
-        lo.a_t.copy_(lo.a_fwd.view(net.r, taps, L.cin).permute(2, 1, 0).reshape(L.cin, taps * net.r))
+    refresh_operands(net)
     ops_interp.install_step(monkeypatch)
     st.load_inputs(_nhwc(batch["latents"]), _nhwc(batch["noise"]), batch["index"], batch["w"],
                    batch["prompt_embeds"].to(BF16), batch["uncond_prompt_embeds"].to(BF16))
@@ -169,3 +161,35 @@ def test_step_host_sequence_matches_the_oracle_iteration(monkeypatch, merge, var
           f"{rel(_nchw(st.debug['eps_student']), ref['eps_student']):.2e} x_prev {rel(_nchw(st.x_prev), ref['x_prev']):.2e} "
           f"| LoRA-gradient cosine {cos:.4f}")
     assert cos >= 0.85          # same bound as the GPU twin (Huber sign noise)
+
+
+def test_sdxl_shaped_step_host_sequence(monkeypatch):
+    """SDXL-shaped network through the whole step on CPU: 40 DDIM steps, added conditions (pooled text
+    embedding + time ids) on every pass, ZERO unconditional embeddings, transformer depth (1, 2, 3) -
+    train_pcm_lora_sdxl_adv.py:1094-1133, 1215-1221.  CPU twin of tests/test_sdxl_gpu.py::test_sdxl_step_loss."""
+    from oracle import pcm_ref, unet_ref
+    from pcm_b200 import config, ops
+    from pcm_b200.step import PCMTrainStep
+    B, hw, mp = 2, 8, 4
+    ocfg = unet_ref.TINY_XL
+    P = unet_ref.init_params(ocfg, 1)
+    batch = pcm_ref.make_batch(ocfg, B, hw, seed=1, num_ddim=40, zero_uncond=True)
+    ref = pcm_ref.pcm_step_ref(ocfg, P, batch, multiphase=mp, num_ddim=40, emulate_bf16=True, need_grad=False)
+    old = ops.DRY_RUN
+    ops.DRY_RUN = []
+    try:
+        st = PCMTrainStep(config.TINY_XL, P, "cpu", batch=B, height=hw, width=hw, multiphase=mp,
+                          num_ddim_timesteps=40, keep_debug=True)
+    finally:
+        ops.DRY_RUN = old
+    refresh_operands(st.unet)
+    ops_interp.install_step(monkeypatch)
+    st.load_inputs(_nhwc(batch["latents"]), _nhwc(batch["noise"]), batch["index"], batch["w"],
+                   batch["prompt_embeds"].to(BF16), batch["uncond_prompt_embeds"].to(BF16),
+                   text_embeds=batch["text_embeds"].to(BF16), time_ids=batch["time_ids"])
+    st.forward_backward()
+    assert torch.equal(st.start_t, ref["start_timesteps"]) and torch.equal(st.end_t, ref["end_timesteps"])
+    rel = lambda a, b: ((a.double() - b.double()).norm() / b.double().norm()).item()  # noqa: E731
+    assert rel(_nchw(st.x_prev), ref["x_prev"]) < 2e-2 and rel(_nchw(st.model_pred), ref["model_pred"]) < 2e-2
+    assert abs(st.loss.item() - ref["loss"].item()) <= 4e-2 * ref["loss"].item()
+    assert st.unet.lora_grad.abs().max() > 0
