@@ -230,6 +230,25 @@ class PcmCalls:
         xp = s["solver"].ddim_step(x0c + w4 * (x0c - x0u), ec + w4 * (ec - eu), s["idx"])
         f(x_prev).copy_(xp.float())
 
+    def pcm_lora_refresh(self, master, table, num_entries, total_work, scale, opnd):
+        """Table-driven regeneration of the bf16 operand copies (csrc/optim.cu lora_refresh_kernel): row =
+        [a_off, b_off, a_fwd, sb_fwd, sb_t, a_t, cin | taps << 32, cout | r << 32, first tile]."""
+        tab = _raw(table, num_entries * 9, ctypes.c_int64, torch.int64).view(num_entries, 9).tolist()
+        work = 0
+        for a_off, b_off, a_fwd, sb_fwd, sb_t, a_t, ci, co, w0 in tab:
+            cin, taps, cout, r = ci & 0xffffffff, ci >> 32, co & 0xffffffff, co >> 32
+            assert r == 64 and w0 == work
+            k = taps * cin
+            A = _raw(master + 4 * a_off, r * k, ctypes.c_float, torch.float32).view(r, k).to(BF16)
+            sB = (_raw(master + 4 * b_off, cout * r, ctypes.c_float, torch.float32).view(cout, r) * scale).to(BF16)
+            o = lambda off, n: _raw(opnd + 2 * off, n, ctypes.c_uint16, torch.int16).view(BF16)  # noqa: E731
+            o(a_fwd, r * k).view(r, k).copy_(A)
+            o(a_t, r * k).view(cin, taps * r).copy_(A.view(r, taps, cin).permute(2, 1, 0).reshape(cin, taps * r))
+            o(sb_fwd, cout * r).view(cout, r).copy_(sB)
+            o(sb_t, cout * r).view(r, cout).copy_(sB.t())
+            work += k // 64 + cout // 64
+        assert work == total_work
+
     def pcm_teacher_substep(self, eps_c, eps_u, x_cur, acp, t_cur, t_next, coef, per, B, pred_type, x_next):
         """one DDIM sub-step t_cur -> t_next of the CFG-mixed prediction (t_next < 0: the solver's
         alpha_cumprods[0] entry), float64 like DDIMSolver.ddim_step"""

@@ -302,3 +302,21 @@ def test_conv_backward_plan(monkeypatch, tiny, name, stride):
     gA = lo.gA.view(net.r, 3, 3, L.cin).permute(0, 3, 1, 2)        # [r, (kh, kw, cin)] -> [r, cin, kh, kw]
     assert _rel(gA, A.grad) < 1e-2
     assert _rel(lo.gB, Bm.grad.reshape(L.cout, net.r)) < 1e-2
+
+
+def test_refresh_table_writes_exactly_the_per_layer_operand_views(tiny):
+    """`pcm_lora_refresh` is driven by an offset table; the GEMM plans read the operand buffer through
+    per-layer and stacked views.  Interpreting the table must reproduce the view-based fill bit for bit
+    and leave no element of the buffer unwritten."""
+    from ops_interp import PcmCalls
+    from gemm_interp import refresh_operands
+    net, _ = tiny
+    want = net.lora_opnd.clone()
+    net.lora_opnd.view(torch.int16).fill_(0x7fc1)            # a NaN pattern no refresh writes
+    PcmCalls().pcm_lora_refresh(net.lora_master.data_ptr(), net.refresh_table.data_ptr(),
+                                net.refresh_table.shape[0], net.refresh_work, net.scale, net.lora_opnd.data_ptr())
+    got = net.lora_opnd.clone()
+    assert not (got.view(torch.int16) == 0x7fc1).any()
+    assert torch.equal(got.view(torch.int16), want.view(torch.int16))
+    refresh_operands(net)
+    assert torch.equal(net.lora_opnd.view(torch.int16), want.view(torch.int16))

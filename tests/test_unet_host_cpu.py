@@ -104,11 +104,13 @@ VARIANTS = {
     "no_cfg_solver": dict(apply_cfg_solver=False),
     "two_substeps": dict(teacher_substeps=2),
     "two_phases": dict(multiphase=2),
+    "ema_target": dict(ema_decay=0.95),      # EMA copy == student at step 0: same numbers, other code path
 }
 
 
 @pytest.mark.parametrize("merge,variant", [("1", "reference"), ("0", "reference"), ("1", "v_prediction_l2"),
-                                           ("1", "no_cfg_solver"), ("1", "two_substeps"), ("1", "two_phases")])
+                                           ("1", "no_cfg_solver"), ("1", "two_substeps"), ("1", "two_phases"),
+                                           ("1", "ema_target")])
 def test_step_host_sequence_matches_the_oracle_iteration(monkeypatch, merge, variant):
     """PCMTrainStep.forward_backward on CPU (every kernel replaced by its torch semantics): merged student +
     teacher pass, teacher DDIM step, target pass on the student's context projections, loss, backward -
@@ -123,7 +125,8 @@ def test_step_host_sequence_matches_the_oracle_iteration(monkeypatch, merge, var
     ocfg = unet_ref.TINY
     P = unet_ref.init_params(ocfg, 0, lora_b_std=0.02)
     batch = pcm_ref.make_batch(ocfg, B, hw, seed=0)
-    ref = pcm_ref.pcm_step_ref(ocfg, P, batch, multiphase=multiphase, emulate_bf16=True, need_grad=True, **kw)
+    okw = {k: v for k, v in kw.items() if k != "ema_decay"}
+    ref = pcm_ref.pcm_step_ref(ocfg, P, batch, multiphase=multiphase, emulate_bf16=True, need_grad=True, **okw)
     old = ops.DRY_RUN
     ops.DRY_RUN = []
     try:
