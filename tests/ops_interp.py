@@ -249,6 +249,33 @@ class PcmCalls:
             work += k // 64 + cout // 64
         assert work == total_work
 
+    def pcm_grad_sumsq(self, g, n, out):
+        _raw(out, 1, ctypes.c_double, torch.float64)[0] = _raw(g, n, ctypes.c_float, torch.float32).double().pow(2).sum()
+
+    def pcm_adamw_clip(self, p, g, m, v, n, state, beta1, beta2, eps, wd, max_norm, inv_world, sumsq, zero_grad):
+        """csrc/optim.cu: step counter += 1 on device, clip coefficient of the MEAN gradient from the sum of
+        squares of the SUMMED gradient, 1/world folded in, torch.optim.AdamW update, optional zero_grad."""
+        f = lambda q: _raw(q, n, ctypes.c_float, torch.float32)  # noqa: E731
+        st = _raw(state, 2, ctypes.c_float, torch.float32)
+        st[1] += 1.0
+        lr, step = st[0].item(), st[1].item()
+        norm = float(_raw(sumsq, 1, ctypes.c_double, torch.float64)[0]) ** 0.5 * inv_world
+        coef = min(max_norm / (norm + 1e-6), 1.0) if max_norm > 0 else 1.0
+        coef *= inv_world
+        P, G, M, V = f(p), f(g), f(m), f(v)
+        gi = G * coef
+        P.mul_(1.0 - lr * wd)
+        M.mul_(beta1).add_(gi, alpha=1.0 - beta1)
+        V.mul_(beta2).addcmul_(gi, gi, value=1.0 - beta2)
+        bc1, bc2 = 1.0 - beta1 ** step, 1.0 - beta2 ** step
+        P.addcdiv_(M, V.sqrt() / bc2 ** 0.5 + eps, value=-lr / bc1)
+        if zero_grad:
+            G.zero_()
+
+    def pcm_ema_update(self, targ, src, n, rate):
+        t = _raw(targ, n, ctypes.c_float, torch.float32)
+        t.mul_(rate).add_(_raw(src, n, ctypes.c_float, torch.float32), alpha=1.0 - rate)
+
     def pcm_teacher_substep(self, eps_c, eps_u, x_cur, acp, t_cur, t_next, coef, per, B, pred_type, x_next):
         """one DDIM sub-step t_cur -> t_next of the CFG-mixed prediction (t_next < 0: the solver's
         alpha_cumprods[0] entry), float64 like DDIMSolver.ddim_step"""
