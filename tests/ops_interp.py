@@ -76,25 +76,29 @@ def _heads(t, B, S, H, D):
 
 
 def attn_fwd(q, k, v, out, lse, B, H, Sq, Skv, D, scale):
-    Q, K, V = _heads(q, B, Sq, H, D), _heads(k, B, Skv, H, D), _heads(v, B, Skv, H, D)
-    s = (Q @ K.transpose(-1, -2)) * scale
-    lse.copy_(torch.logsumexp(s, -1))
-    o = torch.softmax(s, -1) @ V
-    out[:, :H * D].copy_(o.permute(0, 2, 1, 3).reshape(B * Sq, H * D).to(out.dtype))
+    for b in range(B):                      # one sample at a time: [H, Sq, Skv] scores stay small
+        rq, rk = slice(b * Sq, (b + 1) * Sq), slice(b * Skv, (b + 1) * Skv)
+        Q, K, V = _heads(q[rq], 1, Sq, H, D), _heads(k[rk], 1, Skv, H, D), _heads(v[rk], 1, Skv, H, D)
+        s = (Q @ K.transpose(-1, -2)) * scale
+        lse[b].copy_(torch.logsumexp(s, -1)[0])
+        o = torch.softmax(s, -1) @ V
+        out[rq, :H * D].copy_(o.permute(0, 2, 1, 3).reshape(Sq, H * D).to(out.dtype))
     return out
 
 
 def attn_bwd(q, k, v, o, dout, lse, delta, dq, dk, dv, B, H, Sq, Skv, D, scale):
     assert o.stride(0) == dout.stride(0) and dq.stride(0) == q.stride(0)
     assert dk.stride(0) == k.stride(0) and dv.stride(0) == v.stride(0)
-    Q = _heads(q, B, Sq, H, D).requires_grad_(True)
-    K = _heads(k, B, Skv, H, D).requires_grad_(True)
-    V = _heads(v, B, Skv, H, D).requires_grad_(True)
-    with torch.enable_grad():
-        out = torch.softmax((Q @ K.transpose(-1, -2)) * scale, -1) @ V
-        (out * _heads(dout, B, Sq, H, D)).sum().backward()
-    for dst, g, S in ((dq, Q.grad, Sq), (dk, K.grad, Skv), (dv, V.grad, Skv)):
-        dst[:, :H * D].copy_(g.permute(0, 2, 1, 3).reshape(B * S, H * D).to(dst.dtype))
+    for b in range(B):
+        rq, rk = slice(b * Sq, (b + 1) * Sq), slice(b * Skv, (b + 1) * Skv)
+        Q = _heads(q[rq], 1, Sq, H, D).requires_grad_(True)
+        K = _heads(k[rk], 1, Skv, H, D).requires_grad_(True)
+        V = _heads(v[rk], 1, Skv, H, D).requires_grad_(True)
+        with torch.enable_grad():
+            out = torch.softmax((Q @ K.transpose(-1, -2)) * scale, -1) @ V
+            (out * _heads(dout[rq], 1, Sq, H, D)).sum().backward()
+        for dst, g, S, r in ((dq, Q.grad, Sq, rq), (dk, K.grad, Skv, rk), (dv, V.grad, Skv, rk)):
+            dst[r, :H * D].copy_(g.permute(0, 2, 1, 3).reshape(S, H * D).to(dst.dtype))
 
 
 def geglu_fwd(u, out):
