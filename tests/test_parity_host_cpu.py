@@ -85,3 +85,40 @@ def test_config2_host_plan_matches_golden(monkeypatch):
     assert rows["bf16"]["loss"] <= 2e-3 and rows["fp32"]["loss"] <= 1.2e-2
     for k in ("eps", "x_prev", "model_pred", "target"):
         assert rows["bf16"][k] <= 3e-2 and rows["fp32"][k] <= 6e-2, (k, rows)
+
+
+def test_sd15_width_backward_plan_vs_oracle_autograd(monkeypatch):
+    """LoRA gradients of sum(eps * G) for a fixed cotangent G at SD1.5 width (all 278 adapters, bs 1, 32x32):
+    the product's explicit backward walk (dgrad K programs, 1112 weight-gradient launches into the flat
+    buffer) vs torch autograd through the oracle network."""
+    from oracle import pcm_ref, unet_ref
+    from pcm_b200 import config
+    from gemm_interp import build_net
+    B, hw = 1, 32
+    P = unet_ref.init_params(unet_ref.SD15, 0)
+    batch = pcm_ref.make_batch(unet_ref.SD15, B, hw, seed=0)
+    x, ctx = batch["latents"], batch["prompt_embeds"]
+    ts = torch.tensor([499])
+    G = torch.randn(B, 4, hw, hw, generator=torch.Generator().manual_seed(7)) / (B * 4 * hw * hw)
+    Pg = {k: (v.clone().requires_grad_(True) if ".lora_" in k else v) for k, v in P.items()}
+    eps = unet_ref.UNetRef(unet_ref.SD15, Pg, use_lora=True, emulate_bf16=True)(x, ts, ctx)
+    (eps * G).sum().backward()
+    net, _ = build_net(config.SD15, sd=P)
+    ops_interp.install(monkeypatch)
+    out = net.forward(_nhwc(x), ts, ctx.to(BF16).reshape(B * 77, -1), lora=True, save=True)
+    assert _rel(_nchw(out), eps.detach()) <= 3e-2
+    net.lora_grad.zero_()
+    net.backward(_nhwc(G))
+    g = net.lora_grad_dict()
+    num = den = 0.0
+    worst = 0.0
+    n = 0
+    for k, v in Pg.items():
+        if ".lora_" in k:
+            d = (g[k].float() - v.grad.reshape(g[k].shape))
+            num += d.pow(2).sum().item()
+            den += v.grad.pow(2).sum().item()
+            worst = max(worst, (d.norm() / (v.grad.norm() + 1e-20)).item())
+            n += 1
+    print(f"[host backward SD1.5] {n} LoRA tensors: global rel-L2 {(num / den) ** 0.5:.3e}, worst tensor {worst:.3e}")
+    assert n == 2 * 278 and (num / den) ** 0.5 <= 5e-2 and worst <= 0.15
